@@ -1,0 +1,299 @@
+"""gen_golden.py -- generates tests/golden/*.npz by importing and running the UNMODIFIED reference
+from /root/reference (read-only) in the build container. Test infrastructure only.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+
+While generating it also asserts that oracle/minco_ref.py (the Python restatement that travels to
+the GPU box) is bit-identical to the reference on every vector written. The fixtures record the
+numpy/scipy versions because scipy's L-BFGS-B and numpy.linalg.solve are un-pinned third-party
+dependencies of the reference (README.md:43).
+"""
+import contextlib
+import hashlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+import scipy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference/src/planner/scripts'
+sys.path.insert(0, os.path.join(REF, 'traj_planner'))
+sys.path.insert(0, os.path.join(REF, 'map_server'))
+sys.path.insert(0, ROOT)
+
+from expert_planner import MinJerkPlanner, DefaultConfig  # noqa: E402  (reference)
+from esdf import ESDF  # noqa: E402  (reference)
+
+from neo_planner_b200.worlds import make_world, make_problems, YamlConfig  # noqa: E402
+from oracle import minco_ref  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+VERS = np.array([np.__version__, scipy.__version__])
+warnings.filterwarnings('ignore')
+
+
+class _EqSafe(np.ndarray):
+    """numpy >= 2 raises on ``ndarray == []`` (TU:93 `if self.coeffs == []`); older numpy returned False.
+    Viewing coeffs through this subclass restores the old answer so the reference's getters run unmodified."""
+    def __eq__(self, other):
+        if isinstance(other, list) and len(other) == 0:
+            return False
+        return np.ndarray.__eq__(self, other)
+    __hash__ = None
+
+
+class SamplingPlanner(MinJerkPlanner):
+    def get_coeffs(self, int_wpts, ts):
+        super().get_coeffs(int_wpts, ts)
+        self.coeffs = self.coeffs.view(_EqSafe)
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def ref_map(world):
+    e = ESDF()
+    e.occupancy_map_cb(world.occupancy_msg())
+    return e
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def cfg_for(M, base=YamlConfig):
+    c = base()
+    c.init_wpts_num = M - 1
+    return c
+
+
+def gen_esdf():
+    """a20/a21: map build + lookups."""
+    rng = np.random.default_rng(7)
+    H, W, res, ox, oy = 48, 64, 0.1, -1.3, 2.05
+    occ = np.where(rng.random((H, W)) < 0.03, 100, 0).astype(np.int8)
+    occ[rng.random((H, W)) < 0.02] = -1            # unknown cells are free (ESDF:23)
+    from types import SimpleNamespace as NS
+    msg = NS(data=occ.reshape(-1).tolist(),
+             info=NS(resolution=res, width=W, height=H, origin=NS(position=NS(x=ox, y=oy, z=0.0))))
+    e = ESDF()
+    e.occupancy_map_cb(msg)
+    g = minco_ref.GridMap(occ, H, W, res, ox, oy)
+    assert np.array_equal(g.esdf, e.esdf_map) and np.array_equal(g.gx, e.esdf_grad_x) and np.array_equal(g.gy, e.esdf_grad_y)
+    # query points: inside, on cell borders, slightly outside (the (-1,0) truncation quirk), far outside
+    pts = np.concatenate([
+        rng.uniform([ox - 0.3, oy - 0.3], [ox + W * res + 0.3, oy + H * res + 0.3], size=(400, 2)),
+        np.stack([ox + res * rng.integers(-2, W + 2, 100), oy + res * rng.integers(-2, H + 2, 100)], 1),
+        np.array([[ox - 0.05, oy - 0.05], [ox - 0.0999, oy + 1.0], [ox + W * res, oy], [ox + 1.0, oy + H * res - 1e-12]]),
+    ])
+    dis = np.array([e.get_edt_dis(p) for p in pts], dtype=np.float64)
+    grd = np.array([e.get_edt_grad(p) for p in pts], dtype=np.float64)
+    idx = []
+    for p in pts:
+        r = int((p[1] - oy) / res)
+        c = int((p[0] - ox) / res)
+        idx.append((r, c) if (0 <= r < H and 0 <= c < W) else (-1, -1))
+    for p, d0, g0 in zip(pts, dis, grd):
+        assert g.get_edt_dis(p) == d0 and list(g.get_edt_grad(p)) == list(g0)
+    # the all-free map (scipy's implementation-defined answer) and world 0 / dense world hashes
+    free = np.zeros((9, 11), dtype=np.int8)
+    e2 = ESDF()
+    e2.occupancy_map_cb(NS(data=free.reshape(-1).tolist(), info=NS(resolution=0.2, width=11, height=9,
+                                                                     origin=NS(position=NS(x=0.0, y=0.0, z=0.0)))))
+    w0 = make_world(0)
+    e0 = ref_map(w0)
+    np.savez_compressed(os.path.join(OUT, 'esdf_small.npz'), versions=VERS,
+                        occ=occ, H=H, W=W, res=res, ox=ox, oy=oy,
+                        esdf=e.esdf_map, gx=e.esdf_grad_x, gy=e.esdf_grad_y,
+                        pts=pts, dis=dis, grad=grd, idx=np.array(idx, dtype=np.int32),
+                        free_esdf=e2.esdf_map, free_gx=e2.esdf_grad_x, free_gy=e2.esdf_grad_y,
+                        world0_sha=np.array([sha(e0.esdf_map), sha(e0.esdf_grad_x), sha(e0.esdf_grad_y)]),
+                        world0_occ_sha=np.array([sha(w0.occ)]))
+    print('esdf_small.npz')
+
+
+def gen_eval(M, n_prob, name, base=YamlConfig, world_id=0):
+    """a12-a19: cost[4], cost, grad at probe points (x0, perturbed x0, optimum of attempt 0)."""
+    cfg = cfg_for(M, base)
+    w = make_world(world_id)
+    e = ref_map(w)
+    g = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    head, tail = make_problems(w, n_prob, M=M, v_max=cfg.v_max, safe_dis=cfg.safe_dis)
+    pl = MinJerkPlanner(cfg)
+    mine = minco_ref.RefOptimizer(cfg)
+    rng = np.random.default_rng(1234 + M)
+    X, HD, TL, C4, F, GR, CO = [], [], [], [], [], [], []
+    for i in range(n_prob):
+        iw, ts = pl.generate_init_variables(head[i], tail[i])
+        if base is not YamlConfig:
+            ts = ts + 0.7        # library defaults have init_T == T_min (log domain error); shift inside
+        pl.read_planning_conditions(e, head[i], tail[i], iw, ts)
+        mine.set_problem(g, head[i], tail[i], iw, ts)
+        x0 = np.concatenate((iw.reshape(-1), pl.map_T2tau(ts)))
+        probes = [x0]
+        for _ in range(3):
+            dx = np.concatenate((rng.normal(0, 0.4, 2 * (M - 1)), rng.normal(0, 0.8, M)))
+            probes.append(x0 + dx)
+        try:
+            with quiet():
+                pl.plan_once()
+            probes.append(np.concatenate((pl.int_wpts.reshape(-1), pl.tau)))
+        except Exception:
+            pass
+        pl.read_planning_conditions(e, head[i], tail[i], iw, ts)
+        for x in probes:
+            f = pl.get_cost(x)
+            c4 = pl.costs.copy()
+            gr = pl.get_grad(x)
+            assert mine.cost(x) == f and np.array_equal(mine.costs, c4) and np.array_equal(mine.grad(x), gr)
+            X.append(x); HD.append(pl.head_state.copy()); TL.append(pl.tail_state.copy())
+            C4.append(c4); F.append(f); GR.append(gr); CO.append(pl.coeffs.copy())
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, M=M, world_id=world_id,
+                        cfg=np.array([cfg.v_max, cfg.T_min, cfg.T_max, cfg.safe_dis, cfg.delta_t, *cfg.weights,
+                                      cfg.collision_cost_tol, cfg.init_T], dtype=np.float64),
+                        x=np.array(X), head=np.array(HD), tail=np.array(TL), costs=np.array(C4),
+                        f=np.array(F), grad=np.array(GR), coeffs=np.array(CO))
+    print(name, len(X), 'probe points; collision>0 at', int((np.array(C4)[:, 3] > 0).sum()),
+          'feas>0 at', int((np.array(C4)[:, 2] > 0).sum()))
+
+
+def gen_plans(M, n_prob, name, world_id=0):
+    """a9/a10 + a23: plan_once from the expert guess, and full plan() with retries (np.random.seed(k))."""
+    cfg = cfg_for(M)
+    w = make_world(world_id)
+    e = ref_map(w)
+    g = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    head, tail = make_problems(w, n_prob, M=M)
+    n = 2 * (M - 1) + M
+    x0s = np.zeros((n_prob, n)); xs = np.zeros((n_prob, n)); nit = np.zeros(n_prob, np.int32)
+    nfev = np.zeros(n_prob, np.int32); msg = []; c4 = np.zeros((n_prob, 4)); exc = []
+    # full plan() outputs
+    P_ok = np.zeros(n_prob, np.int32); P_x = np.zeros((n_prob, n)); P_ts = np.zeros((n_prob, M))
+    P_coeffs = np.zeros((n_prob, 6 * M, 2)); P_iter = np.zeros(n_prob, np.int32); P_runs = np.zeros(n_prob, np.int32)
+    P_costs = np.zeros((n_prob, 4)); P_cmd_sha = []; P_cmd0 = None
+    for i in range(n_prob):
+        pl = MinJerkPlanner(cfg)
+        mine = minco_ref.RefOptimizer(cfg)
+        iw, ts = pl.generate_init_variables(head[i], tail[i])
+        pl.read_planning_conditions(e, head[i], tail[i], iw, ts)
+        mine.set_problem(g, head[i], tail[i], iw.copy(), ts.copy())
+        x0s[i] = np.concatenate((iw.reshape(-1), pl.map_T2tau(ts)))
+        import scipy.optimize as sopt
+        try:
+            res = sopt.minimize(pl.get_cost, x0s[i], method='L-BFGS-B', jac=pl.get_grad, bounds=None, tol=1e-4,
+                                options={'maxcor': 10, 'maxfun': 15000, 'maxiter': 15000, 'maxls': 20})
+            xs[i] = res.x; nit[i] = res.nit; nfev[i] = res.nfev; msg.append(res.message); c4[i] = pl.costs
+            exc.append('')
+        except Exception as ex:
+            msg.append('EXC'); exc.append(type(ex).__name__)
+        # full plan with reproducible retry noise
+        pl = SamplingPlanner(cfg)
+        np.random.seed(i)
+        try:
+            with quiet():
+                pl.plan(e, head[i], tail[i])
+            P_ok[i] = 1
+            P_x[i] = np.concatenate((pl.int_wpts.reshape(-1), pl.tau)); P_ts[i] = pl.ts
+            P_costs[i] = pl.costs
+            cmd = pl.get_full_state_cmd(60)
+            P_coeffs[i] = np.asarray(pl.coeffs)
+            P_cmd_sha.append(sha(cmd))
+            if P_cmd0 is None:
+                P_cmd0 = (i, cmd)
+        except Exception:
+            P_cmd_sha.append('')
+        P_iter[i] = pl.iter_num; P_runs[i] = pl.opt_running_times
+        # python restatement must reproduce the reference bit for bit (same RNG stream)
+        mine2 = minco_ref.RefOptimizer(cfg)
+        np.random.seed(i)
+        try:
+            mine2.plan(g, head[i], tail[i])
+            ok2 = 1
+        except Exception:
+            ok2 = 0
+        assert ok2 == P_ok[i] and mine2.iter_num == P_iter[i] and mine2.opt_running_times == P_runs[i], (i,)
+        if ok2:
+            assert np.array_equal(np.concatenate((mine2.int_wpts.reshape(-1), mine2.tau)), P_x[i])
+            assert sha(mine2.full_state_cmd(60)) == P_cmd_sha[-1]
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, M=M, world_id=world_id,
+                        head=head, tail=tail, x0=x0s, x=xs, nit=nit, nfev=nfev, msg=np.array(msg), exc=np.array(exc),
+                        costs=c4, plan_ok=P_ok, plan_x=P_x, plan_ts=P_ts, plan_coeffs=P_coeffs, plan_iter=P_iter,
+                        plan_runs=P_runs, plan_costs=P_costs, cmd_index=P_cmd0[0], cmd=P_cmd0[1])
+    print(name, 'messages:', {m: msg.count(m) for m in set(msg)}, 'plan ok', int(P_ok.sum()), '/', n_prob,
+          'mean runs', P_runs.mean())
+
+
+def gen_batch_plan(n_prob, name):
+    """a6/a7: three-candidate batch_plan."""
+    cfg = cfg_for(3)
+    w = make_world(1)
+    e = ref_map(w)
+    g = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    head, tail = make_problems(w, n_prob, M=3)
+    cands = np.zeros((n_prob, 3, 2, 2)); X = np.zeros((n_prob, 4)); TS = np.zeros((n_prob, 3)); FC = np.zeros(n_prob)
+    OK = np.zeros(n_prob, np.int32)
+    for i in range(n_prob):
+        pl = MinJerkPlanner(cfg)
+        cands[i], ts0 = pl.batch_generate_init_variables(head[i], tail[i])
+        np.random.seed(100 + i)
+        try:
+            with quiet():
+                pl.batch_plan(e, head[i], tail[i])
+            OK[i] = 1; X[i] = pl.int_wpts.reshape(-1); TS[i] = pl.ts; FC[i] = pl.final_cost
+        except Exception:
+            pass
+        mine = minco_ref.RefOptimizer(cfg)
+        np.random.seed(100 + i)
+        try:
+            mine.batch_plan(g, head[i], tail[i])
+            assert OK[i] and np.array_equal(mine.int_wpts.reshape(-1), X[i]) and np.array_equal(mine.ts, TS[i])
+        except AssertionError:
+            raise
+        except Exception:
+            assert not OK[i]
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, head=head, tail=tail, cands=cands, ts0=ts0,
+                        ok=OK, int_wpts=X, ts=TS, final_cost=FC)
+    print(name, 'ok', int(OK.sum()), '/', n_prob)
+
+
+def gen_errors(name):
+    """Q11 / a11: error behaviour. Library defaults have init_T == T_min -> ZeroDivisionError on every attempt."""
+    w = make_world(0)
+    e = ref_map(w)
+    head, tail = make_problems(w, 2, M=3)
+    pl = MinJerkPlanner(DefaultConfig())
+    np.random.seed(0)
+    try:
+        with quiet():
+            pl.plan(e, head[0], tail[0])
+        outcome = 'ok'
+    except Exception as ex:
+        outcome = str(ex)
+    # ts outside (T_min, T_max) as an NN guess could produce (EP:209)
+    pl2 = MinJerkPlanner(YamlConfig())
+    iw, ts = pl2.generate_init_variables(head[1], tail[1])
+    bad = ts.copy(); bad[1] = 5.5
+    np.random.seed(3)
+    with quiet():
+        pl2.warm_start_plan(e, head[1], tail[1], iw, bad)
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, head=head, tail=tail,
+                        default_outcome=np.array([outcome]), default_runs=pl.opt_running_times,
+                        bad_ts=bad, bad_x=np.concatenate((pl2.int_wpts.reshape(-1), pl2.tau)), bad_runs=pl2.opt_running_times,
+                        bad_iter=pl2.iter_num)
+    print(name, outcome, pl.opt_running_times, pl2.opt_running_times)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    gen_esdf()
+    gen_eval(3, 24, 'eval_M3.npz')
+    gen_eval(10, 8, 'eval_M10.npz')
+    gen_eval(3, 8, 'eval_M3_libdefaults.npz', base=DefaultConfig)
+    gen_plans(3, 96, 'plans_M3.npz')
+    gen_plans(10, 24, 'plans_M10.npz')
+    gen_batch_plan(16, 'batch_plan_M3.npz')
+    gen_errors('errors.npz')
