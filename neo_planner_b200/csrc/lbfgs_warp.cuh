@@ -1,0 +1,255 @@
+// lbfgs_warp.cuh -- one warp runs scipy.optimize.minimize(method='L-BFGS-B', bounds=None, tol=1e-4,
+// maxcor=10, maxls=20) exactly as the reference calls it (EP:213-225), with the whole optimizer state on chip:
+// lane l < n owns component l of x, g, d and of the saved iterate; the (s, y) history lives in the warp's
+// shared-memory slice; scalar logic (Moré-Thuente dcsrch/dcstep of MINPACK-2, as used by L-BFGS-B 3.0's
+// lnsrlb) is executed redundantly and identically by all 32 lanes. No host round trips.
+//
+// Behaviour restated from scipy 1.18.1 (third-party; `scipy/optimize/_lbfgsb_py.py:336-470`, `_dcsrch.py`):
+//   * ftol = gtol = 1e-4 (tol), factr = ftol/eps; stop if max|g| <= 1e-4 or (f_old-f) <= 1e-4*max(|f_old|,|f|,1)
+//   * direction d = -H g (two-loop recursion, H0 = I/theta, theta = y'y/s'y of the newest pair)
+//   * first step min(1/|d|, 1e10) on iteration 0, else 1; dcsrch(ftol=1e-3, gtol=0.9, xtol=0.1, stpmin=0,
+//     stpmax=1e10); CONVERGENCE and WARNING exits are both accepted; a 21st evaluation request fails the search
+//   * on a failed search: restore x, f, g; if the memory is empty -> ABNORMAL, else drop the memory and retry
+//   * the pair (s, y) is stored unless s'y <= eps * (-g_old's)
+//   * scipy's ScalarFunction does not re-evaluate an x identical to the last evaluated one (nfev bookkeeping)
+#pragma once
+#include "minco_warp.cuh"
+
+namespace neo {
+
+struct Dcsrch {
+    bool brackt;
+    int stage;
+    double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax;
+};
+
+#define LS_FTOL 1e-3
+#define LS_GTOL 0.9
+#define LS_XTOL 0.1
+#define LS_STPMIN 0.0
+#define LS_STPMAX 1e10
+
+__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(a, fmax(b, c)); }
+
+__device__ inline void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
+                              double fp, double dp, bool &brackt, double stpmin, double stpmax)
+{
+    const double sgnd = dp * (dx / fabs(dx));
+    double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+    if (fp > fx) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp < stx) gamma = -gamma;
+        p = (gamma - dx) + theta; q = ((gamma - dx) + gamma) + dp; r = p / q;
+        stpc = stx + r * (stp - stx);
+        stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+        if (fabs(stpc - stx) < fabs(stpq - stx)) stpf = stpc; else stpf = stpc + (stpq - stpc) / 2.0;
+        brackt = true;
+    } else if (sgnd < 0.0) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+        if (stp > stx) gamma = -gamma;
+        p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dx; r = p / q;
+        stpc = stp + r * (stx - stp);
+        stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc; else stpf = stpq;
+        brackt = true;
+    } else if (fabs(dp) < fabs(dx)) {
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+        s = max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+        if (stp > stx) gamma = -gamma;
+        p = (gamma - dp) + theta; q = (gamma + (dx - dp)) + gamma; r = p / q;
+        if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+        else if (stp > stx) stpc = stpmax;
+        else stpc = stpmin;
+        stpq = stp + (dp / (dp - dx)) * (stx - stp);
+        if (brackt) {
+            if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc; else stpf = stpq;
+            if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+            else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+        } else {
+            if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc; else stpf = stpq;
+            stpf = fmin(stpmax, stpf); stpf = fmax(stpmin, stpf);
+        }
+    } else {
+        if (brackt) {
+            theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+            s = max3(fabs(theta), fabs(dy), fabs(dp));
+            gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+            if (stp > sty) gamma = -gamma;
+            p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dy; r = p / q;
+            stpc = stp + r * (sty - stp);
+            stpf = stpc;
+        } else if (stp > stx) stpf = stpmax;
+        else stpf = stpmin;
+    }
+    if (fp > fx) { sty = stp; fy = fp; dy = dp; }
+    else {
+        if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+        stx = stp; fx = fp; dx = dp;
+    }
+    stp = stpf;
+}
+
+__device__ __forceinline__ void dcsrch_start(Dcsrch &S, double stp, double f, double g)
+{
+    S.brackt = false; S.stage = 1; S.finit = f; S.ginit = g; S.gtest = LS_FTOL * g;
+    S.width = LS_STPMAX - LS_STPMIN; S.width1 = S.width / 0.5;
+    S.stx = 0.0; S.fx = f; S.gx = g; S.sty = 0.0; S.fy = f; S.gy = g;
+    S.stmin = 0.0; S.stmax = stp + 4.0 * stp;
+}
+
+// 0 = evaluate at stp, 1 = CONVERGENCE, 2 = WARNING
+__device__ inline int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
+{
+    const double ftest = S.finit + stp * S.gtest;
+    int task = 0;
+    if (S.stage == 1 && f <= ftest && g >= 0.0) S.stage = 2;
+    if (S.brackt && (stp <= S.stmin || stp >= S.stmax)) task = 2;
+    if (S.brackt && S.stmax - S.stmin <= LS_XTOL * S.stmax) task = 2;
+    if (stp == LS_STPMAX && f <= ftest && g <= S.gtest) task = 2;
+    if (stp == LS_STPMIN && (f > ftest || g >= S.gtest)) task = 2;
+    if (f <= ftest && fabs(g) <= LS_GTOL * (-S.ginit)) task = 1;
+    if (task) return task;
+    if (S.stage == 1 && f <= S.fx && f > ftest) {
+        const double fm = f - stp * S.gtest;
+        double fxm = S.fx - S.stx * S.gtest, fym = S.fy - S.sty * S.gtest;
+        const double gm = g - S.gtest;
+        double gxm = S.gx - S.gtest, gym = S.gy - S.gtest;
+        dcstep(S.stx, fxm, gxm, S.sty, fym, gym, stp, fm, gm, S.brackt, S.stmin, S.stmax);
+        S.fx = fxm + S.stx * S.gtest; S.fy = fym + S.sty * S.gtest;
+        S.gx = gxm + S.gtest; S.gy = gym + S.gtest;
+    } else {
+        dcstep(S.stx, S.fx, S.gx, S.sty, S.fy, S.gy, stp, f, g, S.brackt, S.stmin, S.stmax);
+    }
+    if (S.brackt) {
+        if (fabs(S.sty - S.stx) >= 0.66 * S.width1) stp = S.stx + 0.5 * (S.sty - S.stx);
+        S.width1 = S.width; S.width = fabs(S.sty - S.stx);
+    }
+    if (S.brackt) { S.stmin = fmin(S.stx, S.sty); S.stmax = fmax(S.stx, S.sty); }
+    else { S.stmin = stp + 1.1 * (stp - S.stx); S.stmax = stp + 4.0 * (stp - S.stx); }
+    stp = fmax(stp, LS_STPMIN); stp = fmin(stp, LS_STPMAX);
+    if ((S.brackt && (stp <= S.stmin || stp >= S.stmax)) || (S.brackt && S.stmax - S.stmin <= LS_XTOL * S.stmax))
+        stp = S.stx;
+    return 0;
+}
+
+struct OptOut {
+    double x;          // lane l < n: final x[l]
+    double costs[4];   // at the last evaluated point (EP:233)
+    int status, nit, nfev;
+    unsigned long long ns, nv, nc;
+};
+
+// plan_once's minimize() (EP:213-225). x0l: lane l < n holds x0[l].
+__device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
+                                   double x0l, OptOut &o)
+{
+    const int n = 3 * M - 2;
+    const bool mine = lane < n;
+    const double pgtol = 1e-4, ftol = 1e-4, epsmch = 2.220446049250313e-16;
+    const double tol = (ftol / epsmch) * epsmch;
+    const int maxls = 20, maxiter = 15000, maxfun = 15000;
+    double x = mine ? x0l : 0.0, g, d, t, r, xlast;
+    double f, fold, theta = 1.0;
+    int col = 0, head = 0, nit = 0, nfev = 0, st = 0;
+    o.ns = o.nv = o.nc = 0;
+    EvalOut ev;
+    eval_fg(P, map, m, M, lane, x, true, ev);
+    o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
+    if (ev.status) { o.status = ev.status; o.nit = 0; o.nfev = 0; o.x = x; return; }
+    f = ev.f; g = mine ? ev.g : 0.0; nfev = 1; xlast = x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
+    if (warp_max(fabs(g)) <= pgtol) { st = 1; goto done; }
+    for (;;) {
+        // ---- d = -H g -----------------------------------------------------------------------------
+        {
+            double q = g;
+            double al[HIST];
+#pragma unroll
+            for (int k = HIST - 1; k >= 0; k--) {
+                if (k < col) {
+                    const int j = (head + k) % HIST;
+                    const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
+                    al[k] = m.rho[j] * warp_sum(sj * q);
+                    q -= al[k] * yj;
+                }
+            }
+            if (theta != 1.0) q /= theta;
+#pragma unroll
+            for (int k = 0; k < HIST; k++) {
+                if (k < col) {
+                    const int j = (head + k) % HIST;
+                    const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
+                    const double b = m.rho[j] * warp_sum(yj * q);
+                    q += (al[k] - b) * sj;
+                }
+            }
+            d = -q;
+        }
+        // ---- line search (lnsrlb + dcsrch) ----------------------------------------------------------
+        const double dnorm = sqrt(warp_sum(d * d));
+        double stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
+        t = x; r = g; fold = f;
+        double gd = warp_sum(g * d);
+        const double gdold = gd;
+        bool fail = false;
+        if (gd >= 0.0) fail = true;
+        else {
+            Dcsrch ls;
+            dcsrch_start(ls, stp, f, gd);
+            int ifun = 0;
+            for (;;) {
+                ifun++;
+                if (ifun - 1 >= maxls) { fail = true; break; }
+                const double xn = (stp == 1.0) ? (t + d) : (stp * d + t);
+                const bool same = __all_sync(FULL, !mine || xn == xlast);
+                x = xn;
+                if (!same) {
+                    eval_fg(P, map, m, M, lane, x, true, ev);
+                    o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
+                    if (ev.status) { o.status = ev.status; o.nit = nit; o.nfev = nfev; o.x = x; return; }
+                    f = ev.f; g = mine ? ev.g : 0.0; nfev++; xlast = x;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
+                }
+                gd = warp_sum(g * d);
+                if (dcsrch_step(ls, stp, f, gd)) break;
+            }
+        }
+        if (fail) {
+            x = t; g = r; f = fold;
+            if (col == 0) { st = 2; goto done; }
+            col = 0; head = 0; theta = 1.0;
+            continue;
+        }
+        nit++;
+        if (warp_max(fabs(g)) <= pgtol) { st = 1; goto done; }
+        if (fold - f <= tol * max3(fabs(fold), fabs(f), 1.0)) { st = 0; goto done; }
+        if (nit >= maxiter || nfev > maxfun) { st = 3; goto done; }
+        // ---- update the memory (matupd) --------------------------------------------------------------
+        {
+            const double y = g - r;
+            const double rr = warp_sum(y * y);
+            double dr, ddum, s;
+            if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; s = d; }
+            else { dr = (gd - gdold) * stp; s = d * stp; ddum = -gdold * stp; }
+            if (dr <= epsmch * ddum) continue;
+            int slot;
+            if (col < HIST) { slot = (head + col) % HIST; col++; }
+            else { slot = head; head = (head + 1) % HIST; }
+            if (mine) { m.S[slot * n + lane] = s; m.Y[slot * n + lane] = y; }
+            if (lane == 0) m.rho[slot] = 1.0 / dr;
+            theta = rr / dr;
+            __syncwarp();
+        }
+    }
+done:
+    o.x = x; o.status = st; o.nit = nit; o.nfev = nfev;
+}
+
+}  // namespace neo

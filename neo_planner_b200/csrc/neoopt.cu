@@ -1,0 +1,923 @@
+// neoopt.cu -- libneoopt.so: kernels + the C ABI declared in include/neoopt.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py).
+// There is no CPU fallback: without a usable CUDA device neo_create fails with NEO_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/neoopt.h"
+#include "lbfgs_warp.cuh"
+#include "map_kernels.cuh"
+#include "minco_warp.cuh"
+
+using namespace neo;
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WARPS_PER_CTA = 4;
+
+struct OptArgs {
+    int B, M, max_attempts;
+    const double *x0;            // (B,n) tau form
+    const int32_t *x0_status;    // (B) or null: NEO_ST_DOMAIN where map_T2tau failed on the host
+    const double *head, *tail;   // (B,3,2)
+    const int32_t *map_ids;      // (B) or null
+    const double *retry_q;       // (B, A-1, 2(M-1)) or null
+    const double *retry_tau;     // (M) or null
+    int retry_status;            // NEO_ST_DOMAIN if retry_ts is outside (T_min, T_max)
+    const MapView *maps;
+    unsigned int *counter;       // work queue head
+    double *x, *ts, *coeffs, *costs;
+    int32_t *status, *ok, *attempt, *nit, *runs, *nfev;
+    long long *work;
+};
+
+// Persistent warps: each warp pulls problems from a global queue (evaluation counts vary 10..400 per problem)
+// and runs warm_start_plan (EP:186-203) for it entirely on chip.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_optimize(const DevParams P, const OptArgs a)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M;
+    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(a.counter, 1u);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= (unsigned)a.B) break;
+        const size_t b = idx;
+        if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
+        const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
+        __syncwarp();
+        int status = 0, ok = 0, attempt = 0, nit = 0, runs = 0, nfev = 0;
+        unsigned long long ns = 0, nv = 0, nc = 0;
+        double xf = 0.0, costs[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int at = 0; at < a.max_attempts; at++) {
+            attempt = at;
+            double x0l = 0.0;
+            int st0 = 0;
+            if (at == 0) {
+                if (lane < n) x0l = a.x0[b * n + lane];
+                st0 = a.x0_status ? a.x0_status[b] : 0;
+            } else {
+                if (lane < nq) x0l = a.retry_q[(b * (a.max_attempts - 1) + (at - 1)) * nq + lane];
+                else if (lane < n) x0l = a.retry_tau[lane - nq];
+                st0 = a.retry_status;
+            }
+            if (st0) { status = st0; continue; }           // map_T2tau raised (EP:209): attempt lost
+            OptOut o;
+            lbfgsb_warp(P, map, m, M, lane, x0l, o);
+            nfev += o.nfev; ns += o.ns; nv += o.nv; nc += o.nc;
+            status = o.status;
+            if (o.status >= NEO_ST_OVERFLOW) continue;     // exception propagated out of minimize()
+            runs++; nit += o.nit; xf = o.x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) costs[k] = o.costs[k];
+            if (!(costs[3] * P.w3 > P.collision_cost_tol)) { ok = 1; break; }   // EP:235-237
+        }
+        // final (int_wpts, ts) -> ts, coefficients (EP:226-229, TU:182)
+        if (runs > 0) {
+            const double tau = __shfl_sync(FULL, xf, (nq + lane) & 31);
+            if (lane < M) {
+                bool ovf;
+                const double e = exp_dd(-tau, &ovf);
+                m.ts[lane] = (P.T_max - P.T_min) / (1.0 + e) + P.T_min;
+            }
+            __syncwarp();
+            build_system(m, M, lane, xf);
+            factor_and_forward(m, M, lane);
+            solve_U(m, M, lane, m.c);
+            if (lane < n) a.x[b * n + lane] = xf;
+            if (lane < M) a.ts[b * M + lane] = m.ts[lane];
+            for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = m.c[i];
+        } else {
+            if (lane < n) a.x[b * n + lane] = 0.0;
+            if (lane < M) a.ts[b * M + lane] = 0.0;
+            for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = 0.0;
+        }
+        if (lane < 4) a.costs[b * 4 + lane] = costs[lane];
+        if (lane == 0) {
+            a.status[b] = status; a.ok[b] = ok; a.attempt[b] = attempt; a.nit[b] = nit; a.runs[b] = runs;
+            a.nfev[b] = nfev;
+            if (a.work) { a.work[b * 3] = (long long)ns; a.work[b * 3 + 1] = (long long)nv; a.work[b * 3 + 2] = (long long)nc; }
+        }
+        __syncwarp();
+    }
+}
+
+struct EvalArgs {
+    int B, M;
+    const double *x, *head, *tail;
+    const int32_t *map_ids;
+    const MapView *maps;
+    double *costs, *grad, *coeffs, *ts;
+    int32_t *status;
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, const EvalArgs a)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = a.M, n = 3 * M - 2, N = 6 * M;
+    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
+    for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)a.B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
+        if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
+        const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
+        __syncwarp();
+        const double xl = lane < n ? a.x[b * n + lane] : 0.0;
+        EvalOut ev;
+        eval_fg(P, map, m, M, lane, xl, true, ev);
+        if (lane < n) a.grad[b * n + lane] = ev.status ? 0.0 : ev.g;
+        if (lane < 4) a.costs[b * 4 + lane] = ev.costs[lane];
+        if (lane == 0) a.status[b] = ev.status;
+        if (a.coeffs) for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = ev.status == NEO_ST_OVERFLOW ? 0.0 : m.c[i];
+        if (a.ts && lane < M) a.ts[b * M + lane] = m.ts[lane];
+        __syncwarp();
+    }
+}
+
+// get_coeffs (EP:261-336 / TU:8-83): q (B,2,M-1), ts (B,M) -> coeffs (B,6M,2)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_coeffs(int B, int M, const double *q, const double *ts,
+                                                               const double *head, const double *tail, double *coeffs)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nq = 2 * (M - 1), N = 6 * M;
+    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
+    for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
+        if (lane < 6) { m.ht[lane] = head[b * 6 + lane]; m.ht[6 + lane] = tail[b * 6 + lane]; }
+        if (lane < M) m.ts[lane] = ts[b * M + lane];
+        __syncwarp();
+        const double xl = lane < nq ? q[b * nq + lane] : 0.0;
+        build_system(m, M, lane, xl);
+        factor_and_forward(m, M, lane);
+        solve_U(m, M, lane, m.c);
+        for (int i = lane; i < 2 * N; i += 32) coeffs[b * 2 * N + i] = m.c[i];
+        __syncwarp();
+    }
+}
+
+// get_full_state_cmd (TU:181-195): thread per (trajectory b, sample k)
+__global__ void k_sample(int B, int M, const double *__restrict__ coeffs, const double *__restrict__ ts, double hz,
+                         int max_samples, double *__restrict__ states, int32_t *__restrict__ count)
+{
+    const int b = blockIdx.y;
+    const double *T = ts + (size_t)b * M;
+    double total = 0.0;
+    for (int i = 0; i < M; i++) total += T[i];                    // Python sum(self.ts)
+    const double step = 1.0 / hz;
+    const int cnt = (int)ceil(total / step);                      // len(np.arange(0, total, 1/hz))
+    if (blockIdx.x == 0 && threadIdx.x == 0) count[b] = cnt;
+    if (!states) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt && k < max_samples; k += gridDim.x * blockDim.x) {
+        const double t = (double)k * step;
+        int piece = 0;
+        double upto = T[0];                                       // sum(ts[:piece+1]) (TU:97-98)
+        while (upto < t && piece < M - 1) { piece++; upto += T[piece]; }
+        double before = 0.0;
+        for (int i = 0; i < piece; i++) before += T[i];
+        const double s = t - before;
+        const double s2 = s * s, s3 = s2 * s, s4 = s3 * s, s5 = s4 * s;
+        const double *c = coeffs + ((size_t)b * 6 * M + 6 * piece) * 2;
+        double *o = states + ((size_t)b * max_samples + k) * 6;
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            const double c0 = c[d], c1 = c[2 + d], c2 = c[4 + d], c3 = c[6 + d], c4 = c[8 + d], c5 = c[10 + d];
+            o[d] = c0 + c1 * s + c2 * s2 + c3 * s3 + c4 * s4 + c5 * s5;
+            o[2 + d] = c1 + c2 * (2.0 * s) + c3 * (3.0 * s2) + c4 * (4.0 * s3) + c5 * (5.0 * s4);
+            o[4 + d] = c2 * 2.0 + c3 * (6.0 * s) + c4 * (12.0 * s2) + c5 * (20.0 * s3);
+        }
+    }
+}
+
+// FP64 FMA throughput probe: 8 independent accumulators per thread
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// device-side check of exp_dd against the host build of the same header (tests)
+__global__ void k_exp_dd(int n, const double *x, double *y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { bool o; y[i] = exp_dd(x[i], &o); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------
+struct MapSlot {
+    Cell *cells = nullptr;
+    int H = 0, W = 0;
+    double res = 0, ox = 0, oy = 0;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct neo_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    neo_config cfg;
+    std::vector<MapSlot> slots;
+    MapView *d_maps = nullptr;
+    unsigned int *d_counter = nullptr;
+    std::vector<DevBuf> bufs;        // reusable device staging buffers for the host-pointer entry points
+    std::string err;
+    std::mutex mu;
+    float last_ms = 0.f;
+    long long launches = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    char name[128] = {0};
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+            return NEO_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static int fail(neo_handle *h, const char *msg)
+{
+    h->err = msg;
+    return NEO_ERR_INVALID;
+}
+
+static DevParams dev_params(const neo_config &c)
+{
+    DevParams P;
+    P.v_max2 = c.v_max * c.v_max;      // self.v_max**2 (EP:410)
+    P.T_min = c.T_min; P.T_max = c.T_max; P.safe_dis = c.safe_dis; P.dt = c.delta_t;
+    P.w0 = c.weights[0]; P.w1 = c.weights[1]; P.w2 = c.weights[2]; P.w3 = c.weights[3];
+    P.collision_cost_tol = c.collision_cost_tol;
+    return P;
+}
+
+// grow-only device staging buffer #i
+static int dev_buf(neo_handle *h, size_t i, size_t bytes, void **out)
+{
+    if (h->bufs.size() <= i) h->bufs.resize(i + 1);
+    DevBuf &b = h->bufs[i];
+    if (b.cap < bytes) {
+        if (b.p) CK(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+        size_t cap = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return NEO_OK;
+}
+
+static int cfg_check(const neo_config *c)
+{
+    return c && c->delta_t > 0.0 && c->T_max > c->T_min;
+}
+
+extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_handle **out)
+{
+    if (!out || !cfg_check(cfg) || max_maps < 1) { g_create_err = "neo_create: invalid argument"; return NEO_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_err = std::string("neo_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                       "); libneoopt has no CPU fallback";
+        return NEO_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        g_create_err = "neo_create: device is not sm_100 (Blackwell); this library ships sm_100a code only";
+        return NEO_ERR_NO_DEVICE;
+    }
+    neo_handle *h = new neo_handle();
+    h->device = device; h->cfg = *cfg; h->slots.resize(max_maps);
+    h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
+    snprintf(h->name, sizeof(h->name), "%s", prop.name);
+    bool good = cudaSetDevice(device) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess &&
+                cudaMalloc(&h->d_maps, sizeof(MapView) * max_maps) == cudaSuccess &&
+                cudaMemset(h->d_maps, 0, sizeof(MapView) * max_maps) == cudaSuccess &&
+                cudaMalloc(&h->d_counter, sizeof(unsigned int) * 64) == cudaSuccess;
+    if (!good) {
+        g_create_err = std::string("neo_create: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return NEO_ERR_CUDA;
+    }
+    *out = h;
+    return NEO_OK;
+}
+
+extern "C" int neo_destroy(neo_handle *h)
+{
+    if (!h) return NEO_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &s : h->slots) if (s.cells) cudaFree(s.cells);
+    for (auto &b : h->bufs) if (b.p) cudaFree(b.p);
+    cudaFree(h->d_maps); cudaFree(h->d_counter);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return NEO_OK;
+}
+
+extern "C" int neo_set_config(neo_handle *h, const neo_config *cfg)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!cfg_check(cfg)) return fail(h, "neo_set_config: invalid config");
+    h->cfg = *cfg;
+    return NEO_OK;
+}
+
+extern "C" const char *neo_last_error(neo_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int neo_device_info(neo_handle *h, int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len)
+{
+    if (!h) return NEO_ERR_INVALID;
+    if (sm_count) *sm_count = h->sm_count;
+    if (cc_major) *cc_major = h->cc_major;
+    if (cc_minor) *cc_minor = h->cc_minor;
+    if (name && name_len > 0) snprintf(name, name_len, "%s", h->name);
+    return NEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// maps
+// ---------------------------------------------------------------------------------------------------------
+static int slot_prepare(neo_handle *h, int slot, int H, int W, double res, double ox, double oy)
+{
+    if (slot < 0 || slot >= (int)h->slots.size()) return fail(h, "map slot out of range");
+    if (H < 2 || W < 2 || !(res > 0.0)) return fail(h, "map must be at least 2x2 with positive resolution");
+    MapSlot &s = h->slots[slot];
+    if (s.cells && (size_t)s.H * s.W != (size_t)H * W) { CK(cudaFree(s.cells)); s.cells = nullptr; }
+    if (!s.cells) CK(cudaMalloc(&s.cells, sizeof(Cell) * (size_t)H * W));
+    s.H = H; s.W = W; s.res = res; s.ox = ox; s.oy = oy;
+    return NEO_OK;
+}
+
+static int slot_publish(neo_handle *h, int slot)
+{
+    const MapSlot &s = h->slots[slot];
+    MapView v;
+    v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy;
+    CK(cudaMemcpyAsync(h->d_maps + slot, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEO_OK;
+}
+
+extern "C" int neo_set_map_esdf(neo_handle *h, int slot, int H, int W, double res, double ox, double oy,
+                                const double *esdf, const double *gx, const double *gy)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!esdf || !gx || !gy) return fail(h, "neo_set_map_esdf: null array");
+    CK(cudaSetDevice(h->device));
+    int rc = slot_prepare(h, slot, H, W, res, ox, oy);
+    if (rc) return rc;
+    const size_t n = (size_t)H * W;
+    double *d;
+    if ((rc = dev_buf(h, 0, sizeof(double) * 3 * n, (void **)&d))) return rc;
+    CK(cudaMemcpyAsync(d, esdf, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + n, gx, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + 2 * n, gy, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((W + 127) / 128, H);
+    k_pack_cells<<<grid, 128, 0, h->stream>>>(d, d + n, d + 2 * n, H, W, h->slots[slot].cells, nullptr, nullptr);
+    h->launches++;
+    CK(cudaGetLastError());
+    return slot_publish(h, slot);
+}
+
+extern "C" int neo_set_map_occupancy(neo_handle *h, int slot, int H, int W, double res, double ox, double oy,
+                                     const int8_t *occ)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!occ) return fail(h, "neo_set_map_occupancy: null array");
+    if ((long long)H * H + (long long)W * W >= (long long)EDT_INF) return fail(h, "map too large for the int32 EDT");
+    CK(cudaSetDevice(h->device));
+    int rc = slot_prepare(h, slot, H, W, res, ox, oy);
+    if (rc) return rc;
+    const size_t n = (size_t)H * W;
+    char *base;
+    const size_t off_g = (n + 255) & ~(size_t)255, off_any = off_g + sizeof(int) * n, off_e = (off_any + 256 + 255) & ~(size_t)255;
+    if ((rc = dev_buf(h, 0, off_e + sizeof(double) * n, (void **)&base))) return rc;
+    int8_t *d_occ = (int8_t *)base;
+    int *d_g = (int *)(base + off_g), *d_any = (int *)(base + off_any);
+    double *d_e = (double *)(base + off_e);
+    CK(cudaMemcpyAsync(d_occ, occ, n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(d_any, 0, sizeof(int), h->stream));
+    k_edt_rows<<<(H + 63) / 64, 64, 0, h->stream>>>(d_occ, H, W, d_g, d_any);
+    dim3 grid((W + 127) / 128, H);
+    k_edt_cols<<<grid, 128, 0, h->stream>>>(d_g, H, W, d_any, res, d_e);
+    k_pack_cells<<<grid, 128, 0, h->stream>>>(d_e, nullptr, nullptr, H, W, h->slots[slot].cells, nullptr, nullptr);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return slot_publish(h, slot);
+}
+
+extern "C" int neo_get_map(neo_handle *h, int slot, double *esdf, double *gx, double *gy)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (slot < 0 || slot >= (int)h->slots.size() || !h->slots[slot].cells) return fail(h, "neo_get_map: empty slot");
+    CK(cudaSetDevice(h->device));
+    const MapSlot &s = h->slots[slot];
+    const size_t n = (size_t)s.H * s.W;
+    double *d;
+    int rc = dev_buf(h, 0, sizeof(double) * 3 * n, (void **)&d);
+    if (rc) return rc;
+    k_unpack_cells<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(s.cells, n, d, d + n, d + 2 * n);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (esdf) CK(cudaMemcpyAsync(esdf, d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (gx) CK(cudaMemcpyAsync(gx, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (gy) CK(cudaMemcpyAsync(gy, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEO_OK;
+}
+
+extern "C" int neo_query_map(neo_handle *h, int slot, int n, const double *xy, int32_t *idx, double *dis, double *grad)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (slot < 0 || slot >= (int)h->slots.size() || !h->slots[slot].cells) return fail(h, "neo_query_map: empty slot");
+    if (n < 0 || !xy || !idx || !dis || !grad) return fail(h, "neo_query_map: invalid argument");
+    if (n == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    const MapSlot &s = h->slots[slot];
+    char *base;
+    const size_t o_xy = 0, o_idx = sizeof(double) * 2 * n, o_dis = o_idx + sizeof(double) * n /* 8n >= 2*4n */,
+                 o_grad = o_dis + sizeof(double) * n;
+    int rc = dev_buf(h, 1, o_grad + sizeof(double) * 2 * n, (void **)&base);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(base + o_xy, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    MapView v;
+    v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy;
+    k_query<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, (const double *)(base + o_xy), (int32_t *)(base + o_idx),
+                                                    (double *)(base + o_dis), (double *)(base + o_grad));
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(idx, base + o_idx, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(dis, base + o_dis, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(grad, base + o_grad, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------------
+static int check_problem(neo_handle *h, int B, int M)
+{
+    if (B < 0) return fail(h, "B must be >= 0");
+    if (M < 2 || M > NEO_MAX_PIECES) return fail(h, "M must be in [2, NEO_MAX_PIECES]");
+    if (!h->slots[0].cells) {
+        bool any = false;
+        for (auto &s : h->slots) any = any || s.cells;
+        if (!any) return fail(h, "no map uploaded (neo_set_map_esdf / neo_set_map_occupancy)");
+    }
+    return NEO_OK;
+}
+
+static size_t smem_bytes(int M) { return sizeof(double) * (size_t)warp_mem_doubles(M) * WARPS_PER_CTA; }
+
+template <typename K>
+static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm)
+{
+    const size_t smem = smem_bytes(M);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, WARPS_PER_CTA * 32, smem));
+    if (occ < 1) return fail(h, "kernel does not fit on an SM");
+    *ctas_per_sm = occ;
+    return NEO_OK;
+}
+
+static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
+{
+    int occ;
+    int rc = prep_kernel(h, k_optimize, a.M, &occ);
+    if (rc) return rc;
+    const int need = (a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
+    a.maps = h->d_maps;
+    a.counter = h->d_counter;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
+    k_optimize<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return NEO_OK;
+}
+
+static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
+{
+    int occ;
+    int rc = prep_kernel(h, k_eval, a.M, &occ);
+    if (rc) return rc;
+    const int need = (a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
+    a.maps = h->d_maps;
+    k_eval<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return NEO_OK;
+}
+
+// byte-offset bump allocator over one staging buffer
+struct Carver {
+    char *base;
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t count)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? (T *)(base + off) : nullptr;
+        off += sizeof(T) * count;
+        return p;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// eval
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int neo_eval_dev(neo_handle *h, int B, int M, const double *x, const double *head, const double *tail,
+                            const int32_t *map_ids, double *costs, double *grad, int32_t *status, double *coeffs,
+                            double *ts, void *stream)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_problem(h, B, M);
+    if (rc) return rc;
+    if (!x || !head || !tail || !costs || !grad || !status) return fail(h, "neo_eval_dev: null pointer");
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    EvalArgs a;
+    a.B = B; a.M = M; a.x = x; a.head = head; a.tail = tail; a.map_ids = map_ids;
+    a.costs = costs; a.grad = grad; a.status = status; a.coeffs = coeffs; a.ts = ts; a.maps = nullptr;
+    return launch_eval(h, a, stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int neo_eval(neo_handle *h, int B, int M, const double *x, const double *head, const double *tail,
+                        const int32_t *map_ids, double *costs, double *grad, int32_t *status, double *coeffs, double *ts)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_problem(h, B, M);
+    if (rc) return rc;
+    if (!x || !head || !tail || !costs || !grad || !status) return fail(h, "neo_eval: null pointer");
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t n = 3 * M - 2, N2 = 12 * M, b = B;
+    for (int pass = 0; pass < 2; pass++) {
+        Carver c{pass ? (char *)h->bufs[2].p : nullptr};
+        double *d_x = c.take<double>(b * n), *d_head = c.take<double>(b * 6), *d_tail = c.take<double>(b * 6);
+        int32_t *d_ids = c.take<int32_t>(b);
+        double *d_costs = c.take<double>(b * 4), *d_grad = c.take<double>(b * n), *d_coeffs = c.take<double>(b * N2),
+               *d_ts = c.take<double>(b * M);
+        int32_t *d_status = c.take<int32_t>(b);
+        if (!pass) {
+            void *p;
+            if ((rc = dev_buf(h, 2, c.off + 256, &p))) return rc;
+            continue;
+        }
+        cudaStream_t st = h->stream;
+        CK(cudaMemcpyAsync(d_x, x, sizeof(double) * b * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_head, head, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tail, tail, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
+        if (map_ids) CK(cudaMemcpyAsync(d_ids, map_ids, sizeof(int32_t) * b, cudaMemcpyHostToDevice, st));
+        EvalArgs a;
+        a.B = B; a.M = M; a.x = d_x; a.head = d_head; a.tail = d_tail; a.map_ids = map_ids ? d_ids : nullptr;
+        a.costs = d_costs; a.grad = d_grad; a.status = d_status; a.coeffs = coeffs ? d_coeffs : nullptr;
+        a.ts = ts ? d_ts : nullptr; a.maps = nullptr;
+        CK(cudaEventRecord(h->ev0, st));
+        if ((rc = launch_eval(h, a, st))) return rc;
+        CK(cudaEventRecord(h->ev1, st));
+        CK(cudaMemcpyAsync(costs, d_costs, sizeof(double) * b * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(grad, d_grad, sizeof(double) * b * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        if (coeffs) CK(cudaMemcpyAsync(coeffs, d_coeffs, sizeof(double) * b * N2, cudaMemcpyDeviceToHost, st));
+        if (ts) CK(cudaMemcpyAsync(ts, d_ts, sizeof(double) * b * M, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    }
+    return NEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// optimize
+// ---------------------------------------------------------------------------------------------------------
+// map_T2tau (EP:468-475) with the C library's log() -- the function CPython's math.log calls.
+static int T2tau_one(const neo_config *cfg, double T, double *tau)
+{
+    const double den = T - cfg->T_min;
+    if (den == 0.0) return NEO_ST_DOMAIN;
+    const double a = (cfg->T_max - cfg->T_min) / den - 1.0;
+    if (!(a > 0.0) || isinf(a)) return NEO_ST_DOMAIN;
+    *tau = -log(a);
+    return 0;
+}
+
+extern "C" int neo_T2tau(const neo_config *cfg, int n, const double *ts, double *tau, int32_t *status)
+{
+    if (!cfg || n < 0 || !ts || !tau) return NEO_ERR_INVALID;
+    for (int i = 0; i < n; i++) {
+        double t = 0.0;
+        const int st = T2tau_one(cfg, ts[i], &t);
+        tau[i] = st ? 0.0 : t;
+        if (status) status[i] = st;
+    }
+    return NEO_OK;
+}
+
+// internal: device pointers, tau-form inputs
+static int optimize_dev_impl(neo_handle *h, int B, int M, const double *x0, const int32_t *x0_status, const double *head,
+                             const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_tau,
+                             int retry_status, int max_attempts, const neo_result *out, cudaStream_t st)
+{
+    OptArgs a;
+    a.B = B; a.M = M; a.max_attempts = max_attempts;
+    a.x0 = x0; a.x0_status = x0_status; a.head = head; a.tail = tail; a.map_ids = map_ids;
+    a.retry_q = retry_q; a.retry_tau = retry_tau; a.retry_status = retry_status;
+    a.maps = nullptr; a.counter = nullptr;
+    a.x = out->x; a.ts = out->ts; a.coeffs = out->coeffs; a.costs = out->costs;
+    a.status = out->status; a.ok = out->ok; a.attempt = out->attempt; a.nit = out->nit; a.runs = out->runs;
+    a.nfev = out->nfev; a.work = (long long *)out->work;
+    return launch_optimize(h, a, st);
+}
+
+static int result_complete(const neo_result *o)
+{
+    return o && o->x && o->ts && o->coeffs && o->costs && o->status && o->ok && o->attempt && o->nit && o->runs && o->nfev;
+}
+
+// Device-pointer entry. Inputs are in tau form (x0 = [q0, map_T2tau(ts0)], retry_tau = map_T2tau(retry_ts))
+// because map_T2tau must run on the host libm to match the reference bit for bit (see neo_T2tau).
+extern "C" int neo_optimize_dev(neo_handle *h, int B, int M, const double *x0, const int32_t *x0_status,
+                                const double *head, const double *tail, const int32_t *map_ids, const double *retry_q,
+                                const double *retry_tau, int retry_status, int max_attempts, const neo_result *out,
+                                void *stream)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_problem(h, B, M);
+    if (rc) return rc;
+    if (!x0 || !head || !tail || !result_complete(out)) return fail(h, "neo_optimize_dev: null pointer");
+    if (max_attempts < 1 || max_attempts > NEO_MAX_ATTEMPTS) return fail(h, "max_attempts out of range");
+    if (max_attempts > 1 && (!retry_q || !retry_tau)) return fail(h, "retry arrays required when max_attempts > 1");
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    return optimize_dev_impl(h, B, M, x0, x0_status, head, tail, map_ids, retry_q, retry_tau, retry_status, max_attempts,
+                             out, stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
+                            const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
+                            int max_attempts, neo_result *out)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_problem(h, B, M);
+    if (rc) return rc;
+    if (!q0 || !ts0 || !head || !tail || !result_complete(out)) return fail(h, "neo_optimize: null pointer");
+    if (max_attempts < 1 || max_attempts > NEO_MAX_ATTEMPTS) return fail(h, "max_attempts out of range");
+    if (max_attempts > 1 && (!retry_q || !retry_ts)) return fail(h, "retry arrays required when max_attempts > 1");
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t n = 3 * M - 2, nq = 2 * (M - 1), N2 = 12 * M, b = B, A1 = max_attempts - 1;
+
+    // host: x0 = [q0, map_T2tau(ts0)] (EP:207-211)
+    std::vector<double> hx0(b * n);
+    std::vector<int32_t> hst(b);
+    bool any_bad = false;
+    for (size_t i = 0; i < b; i++) {
+        memcpy(&hx0[i * n], q0 + i * nq, sizeof(double) * nq);
+        int st = 0;
+        for (int k = 0; k < M; k++) {
+            double t = 0.0;
+            const int s1 = T2tau_one(&h->cfg, ts0[i * M + k], &t);
+            hx0[i * n + nq + k] = s1 ? 0.0 : t;
+            if (s1) st = s1;
+        }
+        hst[i] = st;
+        any_bad = any_bad || st;
+    }
+    double rtau[NEO_MAX_PIECES] = {0};
+    int rstatus = 0;
+    if (A1) for (int k = 0; k < M; k++) { const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
+
+    for (int pass = 0; pass < 2; pass++) {
+        Carver c{pass ? (char *)h->bufs[3].p : nullptr};
+        double *d_x0 = c.take<double>(b * n), *d_head = c.take<double>(b * 6), *d_tail = c.take<double>(b * 6);
+        int32_t *d_st0 = c.take<int32_t>(b), *d_ids = c.take<int32_t>(b);
+        double *d_rq = c.take<double>(b * A1 * nq + 1), *d_rtau = c.take<double>(NEO_MAX_PIECES);
+        neo_result d;
+        d.x = c.take<double>(b * n); d.ts = c.take<double>(b * M); d.coeffs = c.take<double>(b * N2);
+        d.costs = c.take<double>(b * 4);
+        d.status = c.take<int32_t>(b); d.ok = c.take<int32_t>(b); d.attempt = c.take<int32_t>(b);
+        d.nit = c.take<int32_t>(b); d.runs = c.take<int32_t>(b); d.nfev = c.take<int32_t>(b);
+        d.work = c.take<int64_t>(b * 3);
+        if (!pass) {
+            void *p;
+            if ((rc = dev_buf(h, 3, c.off + 256, &p))) return rc;
+            continue;
+        }
+        cudaStream_t st = h->stream;
+        CK(cudaMemcpyAsync(d_x0, hx0.data(), sizeof(double) * b * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_head, head, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tail, tail, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
+        if (any_bad) CK(cudaMemcpyAsync(d_st0, hst.data(), sizeof(int32_t) * b, cudaMemcpyHostToDevice, st));
+        if (map_ids) CK(cudaMemcpyAsync(d_ids, map_ids, sizeof(int32_t) * b, cudaMemcpyHostToDevice, st));
+        if (A1) {
+            CK(cudaMemcpyAsync(d_rq, retry_q, sizeof(double) * b * A1 * nq, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_rtau, rtau, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+        }
+        if (!out->work) d.work = nullptr;
+        CK(cudaEventRecord(h->ev0, st));
+        rc = optimize_dev_impl(h, B, M, d_x0, any_bad ? d_st0 : nullptr, d_head, d_tail, map_ids ? d_ids : nullptr,
+                               A1 ? d_rq : nullptr, A1 ? d_rtau : nullptr, rstatus, max_attempts, &d, st);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev1, st));
+        CK(cudaMemcpyAsync(out->x, d.x, sizeof(double) * b * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->ts, d.ts, sizeof(double) * b * M, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->coeffs, d.coeffs, sizeof(double) * b * N2, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->costs, d.costs, sizeof(double) * b * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->status, d.status, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->ok, d.ok, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->attempt, d.attempt, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->nit, d.nit, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->runs, d.runs, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->nfev, d.nfev, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        if (out->work) CK(cudaMemcpyAsync(out->work, d.work, sizeof(int64_t) * b * 3, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    }
+    return NEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// coefficients / sampling
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int neo_get_coeffs(neo_handle *h, int B, int M, const double *q, const double *ts, const double *head,
+                              const double *tail, double *coeffs)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (B < 0 || M < 2 || M > NEO_MAX_PIECES) return fail(h, "neo_get_coeffs: B or M out of range");
+    if (!q || !ts || !head || !tail || !coeffs) return fail(h, "neo_get_coeffs: null pointer");
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nq = 2 * (M - 1), N2 = 12 * M, b = B;
+    int rc;
+    for (int pass = 0; pass < 2; pass++) {
+        Carver c{pass ? (char *)h->bufs[4].p : nullptr};
+        double *d_q = c.take<double>(b * nq), *d_ts = c.take<double>(b * M), *d_head = c.take<double>(b * 6),
+               *d_tail = c.take<double>(b * 6), *d_c = c.take<double>(b * N2);
+        if (!pass) {
+            void *p;
+            if ((rc = dev_buf(h, 4, c.off + 256, &p))) return rc;
+            continue;
+        }
+        cudaStream_t st = h->stream;
+        CK(cudaMemcpyAsync(d_q, q, sizeof(double) * b * nq, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_ts, ts, sizeof(double) * b * M, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_head, head, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tail, tail, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
+        int occ;
+        if ((rc = prep_kernel(h, k_coeffs, M, &occ))) return rc;
+        const int need = (B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
+        k_coeffs<<<grid, WARPS_PER_CTA * 32, smem_bytes(M), st>>>(B, M, d_q, d_ts, d_head, d_tail, d_c);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(coeffs, d_c, sizeof(double) * b * N2, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return NEO_OK;
+}
+
+extern "C" int neo_sample(neo_handle *h, int B, int M, const double *coeffs, const double *ts, double hz, int max_samples,
+                          double *states, int32_t *count)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (B < 0 || M < 1 || M > 64 || !(hz > 0.0)) return fail(h, "neo_sample: invalid argument");
+    if (!coeffs || !ts || !count || (states && max_samples < 1)) return fail(h, "neo_sample: null pointer");
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t N2 = 12 * M, b = B, ms = states ? max_samples : 0;
+    int rc;
+    for (int pass = 0; pass < 2; pass++) {
+        Carver c{pass ? (char *)h->bufs[4].p : nullptr};
+        double *d_c = c.take<double>(b * N2), *d_ts = c.take<double>(b * M), *d_s = c.take<double>(b * ms * 6 + 1);
+        int32_t *d_cnt = c.take<int32_t>(b);
+        if (!pass) {
+            void *p;
+            if ((rc = dev_buf(h, 4, c.off + 256, &p))) return rc;
+            continue;
+        }
+        cudaStream_t st = h->stream;
+        CK(cudaMemcpyAsync(d_c, coeffs, sizeof(double) * b * N2, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_ts, ts, sizeof(double) * b * M, cudaMemcpyHostToDevice, st));
+        if (states) CK(cudaMemcpyAsync(d_s, states, sizeof(double) * b * ms * 6, cudaMemcpyHostToDevice, st));
+        dim3 grid(states ? (max_samples + 127) / 128 : 1, B);
+        k_sample<<<grid, 128, 0, st>>>(B, M, d_c, d_ts, hz, max_samples, states ? d_s : nullptr, d_cnt);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(count, d_cnt, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        if (states) CK(cudaMemcpyAsync(states, d_s, sizeof(double) * b * ms * 6, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (states) for (size_t i = 0; i < b; i++) if (count[i] > max_samples) return fail(h, "neo_sample: max_samples too small");
+    }
+    return NEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int neo_last_kernel_ms(neo_handle *h, float *ms)
+{
+    if (!h || !ms) return NEO_ERR_INVALID;
+    *ms = h->last_ms;
+    return NEO_OK;
+}
+
+extern "C" int neo_launch_count(neo_handle *h, int64_t *count)
+{
+    if (!h || !count) return NEO_ERR_INVALID;
+    *count = h->launches;
+    return NEO_OK;
+}
+
+extern "C" int neo_fp64_peak(neo_handle *h, double *tflops)
+{
+    if (!h || !tflops) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    CK(cudaSetDevice(h->device));
+    const int threads = 256, blocks = h->sm_count * 8, iters = 1 << 16;
+    double *d;
+    int rc = dev_buf(h, 5, sizeof(double) * threads * blocks, (void **)&d);
+    if (rc) return rc;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(h->ev0, h->stream));
+        k_fp64_peak<<<blocks, threads, 0, h->stream>>>(d, iters);
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep && ms < best) best = ms;
+        h->launches++;
+    }
+    *tflops = 2.0 * 8.0 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
+    return NEO_OK;
+}
+
+// test hooks: exp_dd on the device and on the host build of the same header
+extern "C" int neo_test_exp_dev(neo_handle *h, int n, const double *x, double *y)
+{
+    if (!h || n < 0 || !x || !y) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    double *d;
+    int rc = dev_buf(h, 5, sizeof(double) * 2 * n, (void **)&d);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    k_exp_dd<<<(n + 255) / 256, 256, 0, h->stream>>>(n, d, d + n);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEO_OK;
+}
+
+extern "C" int neo_test_exp_host(int n, const double *x, double *y)
+{
+    for (int i = 0; i < n; i++) { bool o; y[i] = neo::exp_dd(x[i], &o); }
+    return NEO_OK;
+}
