@@ -253,8 +253,12 @@ def main():
         all_i = torch.zeros(world_size * B * 6, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    stream = torch.cuda.Stream(device=dev)     # a real (non-default) stream: NULL would mean "the handle's own stream"
+    torch.cuda.set_stream(stream)
+
     def step_device():
         st = torch.cuda.current_stream().cuda_stream
+        assert st != 0
         h._ck(h.lib.neo_optimize_dev(h.h, B, M, x0.data_ptr(), None, head.data_ptr(), tail.data_ptr(), None, rq.data_ptr(),
                                      rtau_d.data_ptr(), 0, 5, C.byref(res), C.c_void_p(st)))
         if distributed:

@@ -1,19 +1,25 @@
-// minco_warp.cuh -- one warp = one planning problem: fused get_cost + get_grad of the reference
-// optimizer (EP:539-585) in fp64 on sm_100a.
+// minco_warp.cuh -- one warp = one planning problem: fused get_cost + get_grad of the reference optimizer
+// (EP:539-585) in fp64 on sm_100a.
 //
-//   tau -> T (EP:477-483, double-double exp)             lanes 0..M-1, one piece each
-//   MINCO system A c = b (EP:261-336)                    banded LU, kl = ku = 6, no pivoting, in shared memory
-//   energy / time cost and gradient (EP:345-390)         lanes 0..M-1
-//   sampled feasibility + collision penalties (EP:392-466)  lanes over samples, ESDF cells gathered from L2,
-//                                                        16-value butterfly ("transposed") warp reduction
-//   adjoint A^T G = dW/dc, grad_q, grad_T, grad_tau (EP:494-537, EP:485-492)
+// The reference solves the dense 6M x 6M MINCO system A c = b (EP:261-336, numpy.linalg.solve) and its transpose
+// A^T G = dW/dc (EP:503). Here both are replaced by their exact node-state ("Hermite") reduction:
+//   * each quintic piece is written in terms of its boundary states (p, v, a at both ends) in closed form;
+//   * the only unknowns are (v_j, a_j) at the M-1 interior waypoints, fixed by jerk/snap continuity: a block-
+//     tridiagonal system K u = r with 2x2 blocks, solved by block elimination (M-1 sequential 2x2 steps);
+//   * the adjoint variable G = A^-T dW/dc = dW/db is recovered row by row from the multipliers of K (jerk/snap rows),
+//     the boundary-state gradients h_i = H(T_i)^T dW/dc_i and closed-form sensitivities (pos/vel/acc rows, q rows,
+//     tail rows), and then fed into the reference's own formulas for grad_q and grad_T (EP:506-533) -- including its
+//     re-use of T = ts[M-2] for the last piece.
+// This is algebraically identical to the reference (verified to ~1e-13 against numpy in scratch prototypes and to
+// <= 1e-12 in tests/test_gpu_parity.py) and turns ~6M sequential pivots into M-1 sequential 2x2 blocks.
 //
-// Row order: the reference orders the six rows of interior waypoint i as
-//   [pos=q, pos-cont, vel-cont, acc-cont, jerk-cont, snap-cont]   (rows 6i+3 .. 6i+8, EP:284-316)
-// which puts zeros on the diagonal (numpy pivots). We permute them to
-//   [jerk-cont, snap-cont, pos=q, pos-cont, vel-cont, acc-cont]   (rows 6i+3 .. 6i+8 of P A)
-// so that P A is banded with nonzero pivots and factors without pivoting; G is un-permuted on the fly
-// (reference row 6i+3+a  <->  permuted row 6i+3+PERM[a], PERM = {2,3,4,5,0,1}).
+//   tau -> T (EP:477-483, double-double exp)                       lanes 0..M-1
+//   node blocks, right-hand sides                                   lanes 1..M-1 (one interior node each)
+//   block elimination / back substitution                           lanes 0,1 (one per dimension)
+//   Hermite coefficients, energy cost+gradient (EP:345-390)          lanes 0..2M-1 (piece, dimension)
+//   sampled feasibility + collision penalties (EP:392-466)           all lanes over samples, ESDF cells from L1/L2,
+//                                                                    16-value butterfly ("transposed") warp reduction
+//   adjoint, grad_q, grad_T, grad_tau (EP:485-537)                   lanes (node, dimension) / lanes 0..M-1
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -24,7 +30,6 @@
 namespace neo {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int BW = 13;          // band storage width: offsets -6..+6
 constexpr int HIST = 10;        // L-BFGS memory (maxcor, EP:220)
 
 struct DevParams {
@@ -42,18 +47,27 @@ struct MapView {
     const Cell *cells;
     int H, W;
     double res, ox, oy;
+    double inv_res;
 };
 
-// Per-warp shared-memory slice (all doubles). n = 3M-2 decision variables, N = 6M rows.
+// Per-warp shared-memory slice (all doubles). n = 3M-2 decision variables.
 struct WarpMem {
-    double *Ab;    // [N][BW] band of P A, overwritten by its LU factors
-    double *rinv;  // [N] reciprocals of the U diagonal
-    double *c;     // [N][2] rhs -> polynomial coefficients
-    double *gC;    // [N][2] dW/dc -> adjoint variable (permuted rows)
     double *ts;    // [M]
-    double *ex;    // [M] exp(-tau)
+    double *ex;    // [M]      exp(-tau)
+    double *iT;    // [M][5]   1/T, 1/T^2, ... 1/T^5
     double *gT;    // [M]
-    double *ht;    // [12] head (3,2), tail (3,2)
+    double *P;     // [M+1][2] node positions: head, q_0..q_{M-2}, tail
+    double *U;     // [M+1][4] node (v_x, v_y, a_x, a_y)
+    double *blk;   // [M+1][12] per interior node: L (4), D -> D'^-1 (4), U (4), row-major 2x2
+    double *r;     // [M+1][4] rhs / eta, then r' / eta' : (row0_x, row0_y, row1_x, row1_y)
+    double *lam;   // [M+1][4] multipliers (jerk_x, jerk_y, snap_x, snap_y)
+    double *c;     // [6M][2]  polynomial coefficients
+    double *gC;    // [6M][2]  dW/dc
+    double *h;     // [M][12]  dW/d(boundary state): (ps, vs, as, pe, ve, ae) x (x, y)
+    double *Gs;    // [M+1][10] per interior node: (Gq+Gp, Gv, Ga, lamJ, lamS) x (x, y)
+    double *e0;    // [2M]     energy per (piece, dim)
+    double *gout;  // [n]      gradient staging
+    double *ht;    // [12]     head (3,2), tail (3,2)
     double *S;     // [HIST][n]
     double *Y;     // [HIST][n]
     double *rho;   // [HIST]
@@ -61,30 +75,37 @@ struct WarpMem {
 
 __host__ __device__ inline int warp_mem_doubles(int M)
 {
-    int N = 6 * M, n = 3 * M - 2;
-    int tot = N * BW + N + 2 * N + 2 * N + 3 * M + 12 + 2 * HIST * n + HIST;
+    const int n = 3 * M - 2, M1 = M + 1;
+    int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
+              2 * M + n + 12 + 2 * HIST * n + HIST;
     return (tot + 1) & ~1;
 }
 
 __device__ inline WarpMem carve(double *base, int M)
 {
-    int N = 6 * M, n = 3 * M - 2;
+    const int n = 3 * M - 2, M1 = M + 1;
     WarpMem m;
-    m.Ab = base; base += N * BW;
-    m.rinv = base; base += N;
-    m.c = base; base += 2 * N;
-    m.gC = base; base += 2 * N;
     m.ts = base; base += M;
     m.ex = base; base += M;
+    m.iT = base; base += 5 * M;
     m.gT = base; base += M;
+    m.P = base; base += 2 * M1;
+    m.U = base; base += 4 * M1;
+    m.blk = base; base += 12 * M1;
+    m.r = base; base += 4 * M1;
+    m.lam = base; base += 4 * M1;
+    m.c = base; base += 12 * M;
+    m.gC = base; base += 12 * M;
+    m.h = base; base += 12 * M;
+    m.Gs = base; base += 10 * M1;
+    m.e0 = base; base += 2 * M;
+    m.gout = base; base += n;
     m.ht = base; base += 12;
     m.S = base; base += HIST * n;
     m.Y = base; base += HIST * n;
     m.rho = base;
     return m;
 }
-
-#define AB(r, j) Ab[(r) * BW + ((j) - (r) + 6)]
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -100,8 +121,8 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// Reduce 16 per-lane values over the warp with 16 (not 80) double shuffles: after the call lane l holds
-// in v[0] the warp-wide total of slot (l >> 1).
+// Reduce 16 per-lane values over the warp with 16 (not 80) double shuffles: after the call lane l holds in v[0]
+// the warp-wide total of slot (l >> 1).
 __device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane)
 {
     {
@@ -141,147 +162,108 @@ __device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// MINCO system: build P A and b, factor, solve. (EP:261-336)
+// coefficients: tau -> T was done by the caller (m.ts, m.iT); x component xl in lane l
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void build_system(const WarpMem &m, int M, int lane, double xl)
+
+// Writes node positions / boundary (v,a) from the decision vector and the head/tail states.
+__device__ __forceinline__ void load_nodes(const WarpMem &m, int M, int lane, double xl)
 {
-    const int N = 6 * M, nq = 2 * (M - 1);
-    double *Ab = m.Ab;
-    for (int i = lane; i < N * BW; i += 32) Ab[i] = 0.0;
-    for (int i = lane; i < 2 * N; i += 32) m.c[i] = 0.0;
-    __syncwarp();
-    if (lane < nq) {   // b rows "p_i(T_i) = q_i": x = [q_x(0..M-2), q_y(0..M-2), ...] (EP:211)
-        int d = lane / (M - 1), i = lane - d * (M - 1);
-        m.c[(6 * i + 5) * 2 + d] = xl;
+    const int nq = 2 * (M - 1);
+    if (lane < nq) {   // x = [q_x(0..M-2), q_y(0..M-2), tau] (EP:211): node i+1, dim d
+        const int d = lane / (M - 1), i = lane - d * (M - 1);
+        m.P[2 * (i + 1) + d] = xl;
     }
-    if (lane < 6) {    // head rows 0..2, tail rows N-3..N-1 (EP:274-275)
-        m.c[lane] = m.ht[lane];
-        m.c[(N - 3) * 2 + lane] = m.ht[6 + lane];
-    }
-    if (lane == 31) { AB(0, 0) = 1.0; AB(1, 1) = 1.0; AB(2, 2) = 2.0; }   // EP:277-279
-    if (lane < M) {
-        const double T = m.ts[lane];
-        const double T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
-        if (lane < M - 1) {
-            const int r = 6 * lane + 3, cb = 6 * lane;
-            // jerk continuity (EP:306-309)
-            AB(r, cb + 3) = 6.0; AB(r, cb + 4) = 24.0 * T; AB(r, cb + 5) = 60.0 * T2; AB(r, cb + 9) = -6.0;
-            // snap continuity (EP:310-312)
-            AB(r + 1, cb + 4) = 24.0; AB(r + 1, cb + 5) = 120.0 * T; AB(r + 1, cb + 10) = -24.0;
-            // position at the waypoint (EP:285-290)
-            AB(r + 2, cb) = 1.0; AB(r + 2, cb + 1) = T; AB(r + 2, cb + 2) = T2; AB(r + 2, cb + 3) = T3;
-            AB(r + 2, cb + 4) = T4; AB(r + 2, cb + 5) = T5;
-            // position continuity (EP:291-297)
-            AB(r + 3, cb) = 1.0; AB(r + 3, cb + 1) = T; AB(r + 3, cb + 2) = T2; AB(r + 3, cb + 3) = T3;
-            AB(r + 3, cb + 4) = T4; AB(r + 3, cb + 5) = T5; AB(r + 3, cb + 6) = -1.0;
-            // velocity continuity (EP:298-303)
-            AB(r + 4, cb + 1) = 1.0; AB(r + 4, cb + 2) = 2.0 * T; AB(r + 4, cb + 3) = 3.0 * T2;
-            AB(r + 4, cb + 4) = 4.0 * T3; AB(r + 4, cb + 5) = 5.0 * T4; AB(r + 4, cb + 7) = -1.0;
-            // acceleration continuity (EP:304-308)
-            AB(r + 5, cb + 2) = 2.0; AB(r + 5, cb + 3) = 6.0 * T; AB(r + 5, cb + 4) = 12.0 * T2;
-            AB(r + 5, cb + 5) = 20.0 * T3; AB(r + 5, cb + 8) = -2.0;
-        } else {       // tail rows (EP:318-332)
-            const int r = N - 3, cb = N - 6;
-            AB(r, cb) = 1.0; AB(r, cb + 1) = T; AB(r, cb + 2) = T2; AB(r, cb + 3) = T3; AB(r, cb + 4) = T4;
-            AB(r, cb + 5) = T5;
-            AB(r + 1, cb + 1) = 1.0; AB(r + 1, cb + 2) = 2.0 * T; AB(r + 1, cb + 3) = 3.0 * T2;
-            AB(r + 1, cb + 4) = 4.0 * T3; AB(r + 1, cb + 5) = 5.0 * T4;
-            AB(r + 2, cb + 2) = 2.0; AB(r + 2, cb + 3) = 6.0 * T; AB(r + 2, cb + 4) = 12.0 * T2;
-            AB(r + 2, cb + 5) = 20.0 * T3;
-        }
+    if (lane < 2) {    // head / tail rows (EP:274-275): pos, vel, acc
+        m.P[lane] = m.ht[lane];
+        m.P[2 * M + lane] = m.ht[6 + lane];
+        m.U[lane] = m.ht[2 + lane]; m.U[2 + lane] = m.ht[4 + lane];
+        m.U[4 * M + lane] = m.ht[8 + lane]; m.U[4 * M + 2 + lane] = m.ht[10 + lane];
     }
     __syncwarp();
 }
 
-// In-place banded LU (no pivoting) fused with the forward elimination of the two right-hand sides.
-// Lanes 0..23: row offset ii = lane/4 (6 rows below the pivot), column set {jq, jq+4}, jq = lane%4, out of
-// 8 columns = 6 band columns right of the pivot + the 2 rhs columns.
-__device__ __forceinline__ void factor_and_forward(const WarpMem &m, int M, int lane)
+// Block-tridiagonal system of the interior nodes (jerk + snap continuity), one lane per node, then block elimination
+// by lanes 0/1 (one per dimension). Leaves D'^-1 in m.blk (reused by the adjoint) and the node (v,a) in m.U.
+__device__ __forceinline__ void solve_nodes(const WarpMem &m, int M, int lane)
 {
-    const int N = 6 * M;
-    double *Ab = m.Ab;
-    const int ii = lane >> 2, jq = lane & 3;
-    for (int k = 0; k < N; k++) {
-        const double rk = 1.0 / AB(k, k);
-        if (lane == 31) m.rinv[k] = rk;
-        const int i = k + 1 + ii;
-        double l = 0.0, v0 = 0.0, v1 = 0.0;
-        const bool act = lane < 24 && i < N;
-        const int j0 = k + 1 + jq;                 // band column (jq < 4 < 6)
-        const bool c0 = act && j0 < N;
-        const bool c1band = act && jq < 2 && (j0 + 4) < N;   // second column is a band column
-        const bool c1rhs = act && jq >= 2;                     // second column is rhs dim jq-2
-        if (act) {
-            l = AB(i, k) * rk;
-            if (c0) v0 = AB(i, j0) - l * AB(k, j0);
-            if (c1band) v1 = AB(i, j0 + 4) - l * AB(k, j0 + 4);
-            if (c1rhs) v1 = m.c[i * 2 + (jq - 2)] - l * m.c[k * 2 + (jq - 2)];
+    if (lane >= 1 && lane < M) {
+        const int j = lane;
+        const double a = m.iT[5 * (j - 1)], a2 = m.iT[5 * (j - 1) + 1], a3 = m.iT[5 * (j - 1) + 2], a4 = m.iT[5 * (j - 1) + 3];
+        const double b = m.iT[5 * j], b2 = m.iT[5 * j + 1], b3 = m.iT[5 * j + 2], b4 = m.iT[5 * j + 3];
+        double *B = m.blk + 12 * j;
+        B[0] = -24.0 * a2; B[1] = -3.0 * a; B[2] = -168.0 * a3; B[3] = -24.0 * a2;                       // L_j
+        B[4] = 36.0 * (b2 - a2); B[5] = 9.0 * (a + b); B[6] = -192.0 * (a3 + b3); B[7] = 36.0 * (a2 - b2);   // D_j
+        B[8] = 24.0 * b2; B[9] = -3.0 * b; B[10] = -168.0 * b3; B[11] = 24.0 * b2;                       // U_j
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            const double dm = m.P[2 * j + d] - m.P[2 * (j - 1) + d], dp = m.P[2 * (j + 1) + d] - m.P[2 * j + d];
+            double r0 = 60.0 * (dp * b3 - dm * a3);
+            double r1 = -360.0 * (dm * a4 + dp * b4);
+            if (j == 1) {           // known (v,a) of the head node
+                const double v = m.U[d], ac = m.U[2 + d];
+                r0 -= B[0] * v + B[1] * ac; r1 -= B[2] * v + B[3] * ac;
+            }
+            if (j == M - 1) {       // known (v,a) of the tail node
+                const double v = m.U[4 * M + d], ac = m.U[4 * M + 2 + d];
+                r0 -= B[8] * v + B[9] * ac; r1 -= B[10] * v + B[11] * ac;
+            }
+            m.r[4 * j + d] = r0; m.r[4 * j + 2 + d] = r1;
+        }
+    }
+    __syncwarp();
+    {
+        const int d = lane & 1;
+        double i00 = 0, i01 = 0, i10 = 0, i11 = 0, u00 = 0, u01 = 0, u10 = 0, u11 = 0, p0 = 0, p1 = 0;
+        for (int j = 1; j < M; j++) {
+            const double *B = m.blk + 12 * j;
+            double d00 = B[4], d01 = B[5], d10 = B[6], d11 = B[7];
+            double r0 = m.r[4 * j + d], r1 = m.r[4 * j + 2 + d];
+            if (j > 1) {
+                const double l00 = B[0], l01 = B[1], l10 = B[2], l11 = B[3];
+                const double w00 = l00 * i00 + l01 * i10, w01 = l00 * i01 + l01 * i11;     // W = L_j D'^-1_{j-1}
+                const double w10 = l10 * i00 + l11 * i10, w11 = l10 * i01 + l11 * i11;
+                d00 -= w00 * u00 + w01 * u10; d01 -= w00 * u01 + w01 * u11;
+                d10 -= w10 * u00 + w11 * u10; d11 -= w10 * u01 + w11 * u11;
+                r0 -= w00 * p0 + w01 * p1; r1 -= w10 * p0 + w11 * p1;
+            }
+            const double idet = 1.0 / (d00 * d11 - d01 * d10);
+            i00 = d11 * idet; i01 = -d01 * idet; i10 = -d10 * idet; i11 = d00 * idet;
+            u00 = B[8]; u01 = B[9]; u10 = B[10]; u11 = B[11];
+            p0 = r0; p1 = r1;
+            __syncwarp();
+            if (lane == 0) { double *Bw = m.blk + 12 * j; Bw[4] = i00; Bw[5] = i01; Bw[6] = i10; Bw[7] = i11; }
+            if (lane < 2) { m.r[4 * j + d] = r0; m.r[4 * j + 2 + d] = r1; }
         }
         __syncwarp();
-        if (act) {
-            if (c0) AB(i, j0) = v0;
-            if (c1band) AB(i, j0 + 4) = v1;
-            if (c1rhs) m.c[i * 2 + (jq - 2)] = v1;
-            if (jq == 0) AB(i, k) = l;
+        double v = m.U[4 * M + d], ac = m.U[4 * M + 2 + d];
+        for (int j = M - 1; j >= 1; j--) {
+            const double *B = m.blk + 12 * j;
+            double r0 = m.r[4 * j + d], r1 = m.r[4 * j + 2 + d];
+            if (j < M - 1) { r0 -= B[8] * v + B[9] * ac; r1 -= B[10] * v + B[11] * ac; }
+            v = B[4] * r0 + B[5] * r1; ac = B[6] * r0 + B[7] * r1;
+            if (lane < 2) { m.U[4 * j + d] = v; m.U[4 * j + 2 + d] = ac; }
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
-// U x = y (column sweep, 12 lanes: 6 rows above x 2 dims); v: [N][2]
-__device__ __forceinline__ void solve_U(const WarpMem &m, int M, int lane, double *v)
+// Quintic coefficients of piece i, dimension d from its boundary states (closed-form Hermite inverse).
+__device__ __forceinline__ void hermite_coeffs(const WarpMem &m, int M, int lane)
 {
-    const int N = 6 * M;
-    const double *Ab = m.Ab;
-    const int jj = lane >> 1, d = lane & 1;
-    for (int k = N - 1; k >= 0; k--) {
-        const double xk = v[k * 2 + d] * m.rinv[k];
-        const int i = k - 1 - jj;
-        double nv = 0.0;
-        const bool act = lane < 12 && i >= 0;
-        if (act) nv = v[i * 2 + d] - AB(i, k) * xk;
-        __syncwarp();
-        if (lane < 2) v[k * 2 + d] = xk;
-        if (act) v[i * 2 + d] = nv;
-        __syncwarp();
+    if (lane < 2 * M) {
+        const int i = lane >> 1, d = lane & 1;
+        const double T = m.ts[i], T2 = T * T;
+        const double a3 = m.iT[5 * i + 2], a4 = m.iT[5 * i + 3], a5 = m.iT[5 * i + 4];
+        const double ps = m.P[2 * i + d], pe = m.P[2 * (i + 1) + d];
+        const double vs = m.U[4 * i + d], as = m.U[4 * i + 2 + d], ve = m.U[4 * (i + 1) + d], ae = m.U[4 * (i + 1) + 2 + d];
+        const double dl = pe - ps;
+        double *c = m.c + 12 * i + d;
+        c[0] = ps; c[2] = vs; c[4] = 0.5 * as;
+        c[6] = (20.0 * dl - (8.0 * ve + 12.0 * vs) * T - (3.0 * as - ae) * T2) * (0.5 * a3);
+        c[8] = (-30.0 * dl + (14.0 * ve + 16.0 * vs) * T + (3.0 * as - 2.0 * ae) * T2) * (0.5 * a4);
+        c[10] = (12.0 * dl - 6.0 * (ve + vs) * T - (as - ae) * T2) * (0.5 * a5);
     }
-}
-
-// U^T w = g (forward column sweep); v: [N][2]
-__device__ __forceinline__ void solve_UT(const WarpMem &m, int M, int lane, double *v)
-{
-    const int N = 6 * M;
-    const double *Ab = m.Ab;
-    const int jj = lane >> 1, d = lane & 1;
-    for (int k = 0; k < N; k++) {
-        const double wk = v[k * 2 + d] * m.rinv[k];
-        const int i = k + 1 + jj;
-        double nv = 0.0;
-        const bool act = lane < 12 && i < N;
-        if (act) nv = v[i * 2 + d] - AB(k, i) * wk;
-        __syncwarp();
-        if (lane < 2) v[k * 2 + d] = wk;
-        if (act) v[i * 2 + d] = nv;
-        __syncwarp();
-    }
-}
-
-// L^T z = w (backward column sweep, unit diagonal); v: [N][2]
-__device__ __forceinline__ void solve_LT(const WarpMem &m, int M, int lane, double *v)
-{
-    const int N = 6 * M;
-    const double *Ab = m.Ab;
-    const int jj = lane >> 1, d = lane & 1;
-    for (int k = N - 1; k > 0; k--) {
-        const double zk = v[k * 2 + d];
-        const int i = k - 1 - jj;
-        double nv = 0.0;
-        const bool act = lane < 12 && i >= 0;
-        if (act) nv = v[i * 2 + d] - AB(k, i) * zk;
-        __syncwarp();
-        if (act) v[i * 2 + d] = nv;
-        __syncwarp();
-    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -295,67 +277,72 @@ struct EvalOut {
     unsigned ns, nv, nc;   // samples, velocity-violating samples, colliding samples (work accounting)
 };
 
-// permuted row of reference row 6i+3+a
-__device__ __forceinline__ int perm_row(int i, int a) { return 6 * i + 3 + (a < 4 ? a + 2 : a - 4); }
+// tau -> T for all pieces; returns 0 or the status the reference's exception maps to. Also fills 1/T^k.
+__device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem &m, int M, int lane, double xl,
+                                              double &e_out)
+{
+    const int nq = 2 * (M - 1);
+    const double tau = __shfl_sync(FULL, xl, (nq + lane) & 31);
+    int bad = 0;
+    double e = 0.0;
+    if (lane < M) {
+        bool ovf;
+        e = exp_dd(-tau, &ovf);                               // math.exp(-tau) (EP:481)
+        const double den = (1.0 + e) * (1.0 + e);             // (1+exp(-tau))**2 raises OverflowError (EP:490)
+        if (ovf || den == INFINITY) bad = 4;
+        const double T = (P.T_max - P.T_min) / (1.0 + e) + P.T_min;
+        if (T != T) bad = 6;                                  // int(nan) raises ValueError (EP:401)
+        m.ts[lane] = T;
+        m.ex[lane] = e;
+        const double a = 1.0 / T, a2 = a * a;
+        double *it = m.iT + 5 * lane;
+        it[0] = a; it[1] = a2; it[2] = a2 * a; it[3] = a2 * a2; it[4] = a2 * a2 * a;
+    }
+    e_out = e;
+    bad = __reduce_max_sync(FULL, bad);
+    __syncwarp();
+    return bad;
+}
 
 __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
                                         double xl, bool want_grad, EvalOut &out)
 {
-    const int N = 6 * M, nq = 2 * (M - 1);
+    const int nq = 2 * (M - 1);
     out.status = 0; out.ns = out.nv = out.nc = 0;
     out.g = 0.0;
 
-    // ---- tau -> T (EP:477-483) --------------------------------------------------------------------
-    const double tau = __shfl_sync(FULL, xl, (nq + lane) & 31);
-    int bad = 0;
-    double e = 0.0, T = 1.0;
-    if (lane < M) {
-        bool ovf;
-        e = exp_dd(-tau, &ovf);
-        const double den = (1.0 + e) * (1.0 + e);          // (1+exp(-tau))**2 raises OverflowError (EP:490)
-        if (ovf || den == INFINITY) bad = 4;
-        T = (P.T_max - P.T_min) / (1.0 + e) + P.T_min;
-        if (T != T) bad = 6;                               // int(nan) raises ValueError (EP:401)
-        m.ts[lane] = T;
-        m.ex[lane] = e;
-    }
-    bad = __reduce_max_sync(FULL, bad);
+    double e;
+    int bad = times_from_tau(P, m, M, lane, xl, e);
     if (bad) { out.status = bad; out.f = 0.0; out.costs[0] = out.costs[1] = out.costs[2] = out.costs[3] = 0.0; return; }
-    __syncwarp();
 
     // ---- coefficients (EP:261-336) ----------------------------------------------------------------
-    build_system(m, M, lane, xl);
-    factor_and_forward(m, M, lane);
-    solve_U(m, M, lane, m.c);
+    load_nodes(m, M, lane, xl);
+    solve_nodes(m, M, lane);
+    hermite_coeffs(m, M, lane);
 
-    // ---- energy + time (EP:345-390): lane i < M owns piece i ----------------------------------------
-    double cost0 = 0.0, cost1 = 0.0;
-    if (lane < M) {
-        const double T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
-        const double *ci = m.c + 12 * lane;
-        double gt = P.w1;
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            const double c3 = ci[6 + d], c4 = ci[8 + d], c5 = ci[10 + d];
-            const double r3 = 36.0 * T * c3 + 72.0 * T2 * c4 + 120.0 * T3 * c5;     // rows of beta3_mat @ c
-            const double r4 = 72.0 * T2 * c3 + 192.0 * T3 * c4 + 360.0 * T4 * c5;
-            const double r5 = 120.0 * T3 * c3 + 360.0 * T4 * c4 + 720.0 * T5 * c5;
-            cost0 += c3 * r3 + c4 * r4 + c5 * r5;
-            m.gC[12 * lane + 0 + d] = 0.0; m.gC[12 * lane + 2 + d] = 0.0; m.gC[12 * lane + 4 + d] = 0.0;
-            m.gC[12 * lane + 6 + d] = (P.w0 * 2.0) * r3;
-            m.gC[12 * lane + 8 + d] = (P.w0 * 2.0) * r4;
-            m.gC[12 * lane + 10 + d] = (P.w0 * 2.0) * r5;
-            const double jend = 6.0 * c3 + 24.0 * T * c4 + 60.0 * T2 * c5;         // jerk at the piece end
-            gt += P.w0 * (jend * jend);
-        }
-        m.gT[lane] = gt;
-        cost1 = T;
+    // ---- energy + time (EP:345-390): lane (piece i, dim d) -------------------------------------------
+    if (lane < 2 * M) {
+        const int i = lane >> 1, d = lane & 1;
+        const double T = m.ts[i], T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
+        const double *ci = m.c + 12 * i + d;
+        const double c3 = ci[6], c4 = ci[8], c5 = ci[10];
+        const double r3 = 36.0 * T * c3 + 72.0 * T2 * c4 + 120.0 * T3 * c5;     // rows of beta3_mat @ c
+        const double r4 = 72.0 * T2 * c3 + 192.0 * T3 * c4 + 360.0 * T4 * c5;
+        const double r5 = 120.0 * T3 * c3 + 360.0 * T4 * c4 + 720.0 * T5 * c5;
+        m.e0[lane] = c3 * r3 + c4 * r4 + c5 * r5;
+        double *g = m.gC + 12 * i + d;
+        g[0] = 0.0; g[2] = 0.0; g[4] = 0.0;
+        g[6] = (P.w0 * 2.0) * r3; g[8] = (P.w0 * 2.0) * r4; g[10] = (P.w0 * 2.0) * r5;
+        const double jend = 6.0 * c3 + 24.0 * T * c4 + 60.0 * T2 * c5;         // jerk at the piece end
+        const double je2 = P.w0 * (jend * jend);
+        const double other = __shfl_xor_sync(0xffffffffu >> (32 - 2 * M), je2, 1);
+        if (d == 0) m.gT[i] = (je2 + other) + P.w1;
     }
     __syncwarp();
     double costs0 = 0.0, costs1 = 0.0;
     for (int i = 0; i < M; i++) {          // sequential, like the reference's loops / np.sum
-        costs0 += __shfl_sync(FULL, cost0, i);
-        costs1 += __shfl_sync(FULL, cost1, i);
+        costs0 += m.e0[2 * i] + m.e0[2 * i + 1];
+        costs1 += m.ts[i];
     }
 
     // ---- sampled penalties (EP:392-466): lanes over the samples of one piece at a time ---------------
@@ -363,6 +350,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     for (int i = 0; i < M; i++) {
         const double Ti = m.ts[i];
         const int ns = (int)(Ti / P.dt);                    // int(T/delta_t) (EP:401)
+        const double inv_ns = 1.0 / (double)ns;
         const double *ci = m.c + 12 * i;
         double cx[6], cy[6];
 #pragma unroll
@@ -370,38 +358,37 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         double acc[16];
 #pragma unroll
         for (int s = 0; s < 16; s++) acc[s] = 0.0;
-        const double inv_ns = 1.0;   // divisions kept explicit below to follow the reference's rounding
-        (void)inv_ns;
-        for (int j0 = 0; j0 < ns; j0 += 32) {
-            const int j = j0 + lane;
-            const bool live = j < ns;
+        for (int j = lane; j < ns; j += 32) {
             const double t = (double)j * P.dt;               // np.arange(0, T_max, dt)[j] (EP:251)
-            const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+            const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
             const double px = cx[0] + cx[1] * t + cx[2] * t2 + cx[3] * t3 + cx[4] * t4 + cx[5] * t5;
             const double py = cy[0] + cy[1] * t + cy[2] * t2 + cy[3] * t3 + cy[4] * t4 + cy[5] * t5;
             const double b1[6] = {0.0, 1.0, 2.0 * t, 3.0 * t2, 4.0 * t3, 5.0 * t4};
             const double vx = cx[1] + cx[2] * b1[2] + cx[3] * b1[3] + cx[4] * b1[4] + cx[5] * b1[5];
             const double vy = cy[1] + cy[2] * b1[2] + cy[3] * b1[3] + cy[4] * b1[4] + cy[5] * b1[5];
             const double omg = (j == 0 || j == ns - 1) ? 0.5 : 1.0;   // EP:407
-            // feasibility (EP:409-413, EP:441-451)
-            const double vv = (vx * vx + vy * vy) - P.v_max2;
-            const bool viol_v = live && vv > 0.0;
-            // collision (EP:415-422, EP:453-466): nearest-cell lookup, trunc-toward-zero index (ESDF:61-65)
-            const double fr = (py - map.oy) / map.res;
-            const double fc = (px - map.ox) / map.res;
-            if (live && (fr != fr || fc != fc)) bad = 6;       // int(nan) raises ValueError
+            // collision lookup (EP:415-417): nearest cell, index = int((p - origin)/res), trunc toward zero
+            // (ESDF:61-65). The quotient is first formed with the reciprocal; the exact IEEE division is only
+            // redone when that estimate is within 1e-9 of an integer, so the truncated index is always the
+            // reference's.
+            const double dy = py - map.oy, dx = px - map.ox;
+            double fr = dy * map.inv_res, fc = dx * map.inv_res;
+            if (fabs(fr - rint(fr)) < 1e-9 * fmax(1.0, fabs(fr))) fr = dy / map.res;
+            if (fabs(fc - rint(fc)) < 1e-9 * fmax(1.0, fabs(fc))) fc = dx / map.res;
+            if (fr != fr || fc != fc) bad = 6;                 // int(nan) raises ValueError
             const double tr = trunc(fr), tc = trunc(fc);
-            const bool inside = live && tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W;
+            const bool inside = tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W;
             double dis = 10000.0;
             const Cell *cell = map.cells;
             if (inside) {
                 cell = map.cells + ((size_t)(int)tr * map.W + (int)tc);
                 dis = __ldg(&cell->d);
             }
+            // feasibility (EP:409-413, EP:441-451)
+            const double vv = (vx * vx + vy * vy) - P.v_max2;
             const double vd = P.safe_dis - dis;
-            const bool viol_d = inside && vd > 0.0;
-            out.ns += live ? 1u : 0u;
-            if (viol_v) {
+            out.ns++;
+            if (vv > 0.0) {
                 const double vv2 = vv * vv, vv3 = vv2 * vv;
                 acc[13] += (omg * P.dt) * vv3;
                 if (want_grad) {
@@ -412,11 +399,11 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
                     const double kx = (P.w2 * K) * (2.0 * vx), ky = (P.w2 * K) * (2.0 * vy);
 #pragma unroll
                     for (int k = 1; k < 6; k++) { acc[2 * k] += b1[k] * kx; acc[2 * k + 1] += b1[k] * ky; }
-                    acc[12] += P.w2 * (omg * vv3 / (double)ns + K * v2t * (double)j / (double)ns);
+                    acc[12] += P.w2 * ((omg * vv3 + K * v2t * (double)j) * inv_ns);
                 }
                 out.nv++;
             }
-            if (viol_d) {
+            if (vd > 0.0) {       // collision (EP:418-422, EP:453-466); outside the map dis = 10000 never violates
                 const double vd2 = vd * vd, vd3 = vd2 * vd;
                 acc[14] += (omg * P.dt) * vd3;
                 if (want_grad) {
@@ -427,7 +414,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
                     const double b0[6] = {1.0, t, t2, t3, t4, t5};
 #pragma unroll
                     for (int k = 0; k < 6; k++) { acc[2 * k] += b0[k] * kx; acc[2 * k + 1] += b0[k] * ky; }
-                    acc[12] += P.w3 * (omg * vd3 / (double)ns + K * p2t * (double)j / (double)ns);
+                    acc[12] += P.w3 * ((omg * vd3 + K * p2t * (double)j) * inv_ns);
                 }
                 out.nc++;
             }
@@ -452,20 +439,82 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     if (!want_grad) return;
     __syncwarp();
 
-    // ---- adjoint (EP:494-537): A^T G = dW/dc with P A = L U  =>  U^T L^T (P G) = dW/dc -----------------
-    solve_UT(m, M, lane, m.gC);
-    solve_LT(m, M, lane, m.gC);
-    const double *z = m.gC;     // z[perm_row] = G[reference row]
-    double g_out = 0.0;
-    if (lane < nq) {             // grad_q[d][i] = G[6i+3][d] (EP:506-508)
-        const int d = lane / (M - 1), i = lane - d * (M - 1);
-        g_out = z[perm_row(i, 0) * 2 + d];
+    // ---- adjoint (EP:494-537) ------------------------------------------------------------------------
+    // h_i = H(T_i)^T dW/dc_i: gradient w.r.t. the boundary states of piece i, lane (i, d)
+    if (lane < 2 * M) {
+        const int i = lane >> 1, d = lane & 1;
+        const double a = m.iT[5 * i], a2 = m.iT[5 * i + 1], a3 = m.iT[5 * i + 2], a4 = m.iT[5 * i + 3], a5 = m.iT[5 * i + 4];
+        const double *g = m.gC + 12 * i + d;
+        const double g0 = g[0], g1 = g[2], g2 = g[4], g3 = g[6], g4 = g[8], g5 = g[10];
+        double *h = m.h + 12 * i + d;
+        const double pe = 10.0 * a3 * g3 - 15.0 * a4 * g4 + 6.0 * a5 * g5;
+        h[0] = g0 - pe;
+        h[2] = g1 - 6.0 * a2 * g3 + 8.0 * a3 * g4 - 3.0 * a4 * g5;
+        h[4] = 0.5 * g2 - 1.5 * a * g3 + 1.5 * a2 * g4 - 0.5 * a3 * g5;
+        h[6] = pe;
+        h[8] = -4.0 * a2 * g3 + 7.0 * a3 * g4 - 3.0 * a4 * g5;
+        h[10] = 0.5 * a * g3 - a2 * g4 + 0.5 * a3 * g5;
     }
+    __syncwarp();
+    // eta_j = dW/d(v_j, a_j) at the interior nodes, then K^T lam = eta by block elimination (lanes 0/1 per dim);
+    // the Schur complements of K^T are the transposes of those of K, so D'^-1 from the forward solve is reused.
+    {
+        const int d = lane & 1;
+        double y0 = 0.0, y1 = 0.0;      // y_{j-1} = D'^-T_{j-1} eta'_{j-1}
+        for (int j = 1; j < M; j++) {
+            const double *B = m.blk + 12 * j;
+            double e0 = m.h[12 * (j - 1) + 8 + d] + m.h[12 * j + 2 + d];
+            double e1 = m.h[12 * (j - 1) + 10 + d] + m.h[12 * j + 4 + d];
+            if (j > 1) {
+                const double *Bp = m.blk + 12 * (j - 1);
+                e0 -= Bp[8] * y0 + Bp[10] * y1;          // U_{j-1}^T y
+                e1 -= Bp[9] * y0 + Bp[11] * y1;
+            }
+            y0 = B[4] * e0 + B[6] * e1;                  // D'^-T eta'
+            y1 = B[5] * e0 + B[7] * e1;
+            if (lane < 2) { m.r[4 * j + d] = y0; m.r[4 * j + 2 + d] = y1; }
+        }
+        __syncwarp();
+        double l0 = 0.0, l1 = 0.0;
+        for (int j = M - 1; j >= 1; j--) {
+            const double *B = m.blk + 12 * j;
+            double s0 = m.r[4 * j + d], s1 = m.r[4 * j + 2 + d];
+            if (j < M - 1) {
+                const double *Bn = m.blk + 12 * (j + 1);
+                const double t0 = Bn[0] * l0 + Bn[2] * l1, t1 = Bn[1] * l0 + Bn[3] * l1;    // L_{j+1}^T lam_{j+1}
+                s0 -= B[4] * t0 + B[6] * t1;             // D'^-T (.)
+                s1 -= B[5] * t0 + B[7] * t1;
+            }
+            l0 = s0; l1 = s1;
+            if (lane < 2) { m.lam[4 * j + d] = l0; m.lam[4 * j + 2 + d] = l1; }
+        }
+        if (lane < 2) { m.lam[d] = 0.0; m.lam[2 + d] = 0.0; m.lam[4 * M + d] = 0.0; m.lam[4 * M + 2 + d] = 0.0; }
+    }
+    __syncwarp();
+    // G rows of interior node j (reference rows 6(j-1)+3 .. 6(j-1)+8), lane (j, d): grad_q and the T-gradient inputs
+    if (lane >= 2 && lane < 2 * M) {
+        const int j = lane >> 1, d = lane & 1;
+        const double a3 = m.iT[5 * (j - 1) + 2], a4 = m.iT[5 * (j - 1) + 3];
+        const double b = m.iT[5 * j], b2 = m.iT[5 * j + 1], b3 = m.iT[5 * j + 2], b4 = m.iT[5 * j + 3];
+        const double lJ = m.lam[4 * j + d], lS = m.lam[4 * j + 2 + d];
+        const double lJm = m.lam[4 * (j - 1) + d], lSm = m.lam[4 * (j - 1) + 2 + d];        // zero at node 0
+        const double lJp = m.lam[4 * (j + 1) + d], lSp = m.lam[4 * (j + 1) + 2 + d];        // zero at node M
+        const double *hj = m.h + 12 * j + d, *hm = m.h + 12 * (j - 1) + d;
+        const double Gp = -hj[0] - (-60.0 * b3 * lJ + 360.0 * b4 * lS) + (-60.0 * b3 * lJp - 360.0 * b4 * lSp);
+        const double Gv = -hj[2] - (-36.0 * b2 * lJ + 192.0 * b3 * lS) + (-24.0 * b2 * lJp - 168.0 * b3 * lSp);
+        const double Ga = -hj[4] - (-9.0 * b * lJ + 36.0 * b2 * lS) + (-3.0 * b * lJp - 24.0 * b2 * lSp);
+        const double Gq = hm[6] + hj[0] + (60.0 * a3 * lJm - 360.0 * a4 * lSm)
+                        - ((60.0 * a3 + 60.0 * b3) * lJ + (360.0 * a4 - 360.0 * b4) * lS)
+                        - (-60.0 * b3 * lJp - 360.0 * b4 * lSp);
+        double *G = m.Gs + 10 * j + d;
+        G[0] = Gq + Gp; G[2] = Gv; G[4] = Ga; G[6] = lJ; G[8] = lS;
+        m.gout[d * (M - 1) + (j - 1)] = Gq;              // grad_q[d][j-1] = G[6(j-1)+3][d] (EP:506-508)
+    }
+    __syncwarp();
     // grad_T (EP:511-533): piece i < M-1 uses T_i; the last piece re-uses the loop variable T = ts[M-2]
-    double gtau = 0.0;
     if (lane < M) {
         const int i = lane;
-        const double Tq = (i < M - 1) ? T : m.ts[M - 2];
+        const double Tq = (i < M - 1) ? m.ts[i] : m.ts[M - 2];
         const double T2 = Tq * Tq, T3 = T2 * Tq, T4 = T3 * Tq;
         const double *ci = m.c + 12 * i;
         double tr = 0.0;
@@ -478,22 +527,24 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
             if (i < M - 1) {
                 const double sn = 24.0 * c4 + 120.0 * Tq * c5;
                 const double cr = 120.0 * c5;
-                tr += (z[perm_row(i, 0) * 2 + d] + z[perm_row(i, 1) * 2 + d]) * vel + z[perm_row(i, 2) * 2 + d] * ac
-                    + z[perm_row(i, 3) * 2 + d] * jr + z[perm_row(i, 4) * 2 + d] * sn + z[perm_row(i, 5) * 2 + d] * cr;
-            } else {
-                tr += z[(N - 3) * 2 + d] * vel + z[(N - 2) * 2 + d] * ac + z[(N - 1) * 2 + d] * jr;
+                const double *G = m.Gs + 10 * (i + 1) + d;
+                tr += G[0] * vel + G[2] * ac + G[4] * jr + G[6] * sn + G[8] * cr;
+            } else {      // tail rows: G[-3:] = dW/d(tail pos, vel, acc)
+                const double b = m.iT[5 * i], b2 = m.iT[5 * i + 1], b3 = m.iT[5 * i + 2], b4 = m.iT[5 * i + 3];
+                const double lJ = m.lam[4 * i + d], lS = m.lam[4 * i + 2 + d];      // multipliers of node M-1 (0 if M = 1)
+                const double *h = m.h + 12 * i + d;
+                const double Gtp = h[6] + 60.0 * b3 * lJ - 360.0 * b4 * lS;
+                const double Gtv = h[8] - 24.0 * b2 * lJ + 168.0 * b3 * lS;
+                const double Gta = h[10] + 3.0 * b * lJ - 24.0 * b2 * lS;
+                tr += Gtp * vel + Gtv * ac + Gta * jr;
             }
         }
         const double gTi = m.gT[i] - tr;
-        gtau = gTi * (P.T_max - P.T_min) * e / ((1.0 + e) * (1.0 + e));      // EP:485-492
+        m.gout[nq + i] = gTi * (P.T_max - P.T_min) * e / ((1.0 + e) * (1.0 + e));      // EP:485-492
     }
-    // place grad_tau[i] (held by lane i) into lane nq+i
-    const double gt_sh = __shfl_sync(FULL, gtau, (lane - nq) & 31);
-    if (lane >= nq && lane < nq + M) g_out = gt_sh;
-    out.g = g_out;
+    __syncwarp();
+    out.g = (lane < nq + M) ? m.gout[lane] : 0.0;
     __syncwarp();
 }
-
-#undef AB
 
 }  // namespace neo

@@ -84,16 +84,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_optimize(const DevParams
         }
         // final (int_wpts, ts) -> ts, coefficients (EP:226-229, TU:182)
         if (runs > 0) {
-            const double tau = __shfl_sync(FULL, xf, (nq + lane) & 31);
-            if (lane < M) {
-                bool ovf;
-                const double e = exp_dd(-tau, &ovf);
-                m.ts[lane] = (P.T_max - P.T_min) / (1.0 + e) + P.T_min;
-            }
-            __syncwarp();
-            build_system(m, M, lane, xf);
-            factor_and_forward(m, M, lane);
-            solve_U(m, M, lane, m.c);
+            double e_unused;
+            times_from_tau(P, m, M, lane, xf, e_unused);
+            load_nodes(m, M, lane, xf);
+            solve_nodes(m, M, lane);
+            hermite_coeffs(m, M, lane);
             if (lane < n) a.x[b * n + lane] = xf;
             if (lane < M) a.ts[b * M + lane] = m.ts[lane];
             for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = m.c[i];
@@ -153,12 +148,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_coeffs(int B, int M, con
     const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
     for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
         if (lane < 6) { m.ht[lane] = head[b * 6 + lane]; m.ht[6 + lane] = tail[b * 6 + lane]; }
-        if (lane < M) m.ts[lane] = ts[b * M + lane];
+        if (lane < M) {
+            const double T = ts[b * M + lane];
+            m.ts[lane] = T;
+            const double a = 1.0 / T, a2 = a * a;
+            double *it = m.iT + 5 * lane;
+            it[0] = a; it[1] = a2; it[2] = a2 * a; it[3] = a2 * a2; it[4] = a2 * a2 * a;
+        }
         __syncwarp();
         const double xl = lane < nq ? q[b * nq + lane] : 0.0;
-        build_system(m, M, lane, xl);
-        factor_and_forward(m, M, lane);
-        solve_U(m, M, lane, m.c);
+        load_nodes(m, M, lane, xl);
+        solve_nodes(m, M, lane);
+        hermite_coeffs(m, M, lane);
         for (int i = lane; i < 2 * N; i += 32) coeffs[b * 2 * N + i] = m.c[i];
         __syncwarp();
     }
@@ -384,7 +385,7 @@ static int slot_publish(neo_handle *h, int slot)
 {
     const MapSlot &s = h->slots[slot];
     MapView v;
-    v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy;
+    v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy; v.inv_res = 1.0 / s.res;
     CK(cudaMemcpyAsync(h->d_maps + slot, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return NEO_OK;
@@ -477,7 +478,7 @@ extern "C" int neo_query_map(neo_handle *h, int slot, int n, const double *xy, i
     if (rc) return rc;
     CK(cudaMemcpyAsync(base + o_xy, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
     MapView v;
-    v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy;
+    v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy; v.inv_res = 1.0 / s.res;
     k_query<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, (const double *)(base + o_xy), (int32_t *)(base + o_idx),
                                                     (double *)(base + o_dis), (double *)(base + o_grad));
     h->launches++;
