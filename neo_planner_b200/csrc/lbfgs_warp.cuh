@@ -114,16 +114,14 @@ __device__ inline int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
     if (stp == LS_STPMIN && (f > ftest || g >= S.gtest)) task = 2;
     if (f <= ftest && fabs(g) <= LS_GTOL * (-S.ginit)) task = 1;
     if (task) return task;
-    if (S.stage == 1 && f <= S.fx && f > ftest) {
-        const double fm = f - stp * S.gtest;
-        double fxm = S.fx - S.stx * S.gtest, fym = S.fy - S.sty * S.gtest;
-        const double gm = g - S.gtest;
-        double gxm = S.gx - S.gtest, gym = S.gy - S.gtest;
+    {   // a modified function is used in stage 1 while the decrease is not yet sufficient
+        const bool mod = S.stage == 1 && f <= S.fx && f > ftest;
+        const double gt = mod ? S.gtest : 0.0;
+        const double fm = f - stp * gt, gm = g - gt;
+        double fxm = S.fx - S.stx * gt, fym = S.fy - S.sty * gt, gxm = S.gx - gt, gym = S.gy - gt;
         dcstep(S.stx, fxm, gxm, S.sty, fym, gym, stp, fm, gm, S.brackt, S.stmin, S.stmax);
-        S.fx = fxm + S.stx * S.gtest; S.fy = fym + S.sty * S.gtest;
-        S.gx = gxm + S.gtest; S.gy = gym + S.gtest;
-    } else {
-        dcstep(S.stx, S.fx, S.gx, S.sty, S.fy, S.gy, stp, f, g, S.brackt, S.stmin, S.stmax);
+        S.fx = fxm + S.stx * gt; S.fy = fym + S.sty * gt;
+        S.gx = gxm + gt; S.gy = gym + gt;
     }
     if (S.brackt) {
         if (fabs(S.sty - S.stx) >= 0.66 * S.width1) stp = S.stx + 0.5 * (S.sty - S.stx);
@@ -145,6 +143,7 @@ struct OptOut {
 };
 
 // plan_once's minimize() (EP:213-225). x0l: lane l < n holds x0[l].
+// Written as a state machine around ONE evaluation site so the (large) fused evaluator is instantiated once.
 __device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
                                    double x0l, OptOut &o)
 {
@@ -153,100 +152,99 @@ __device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const
     const double pgtol = 1e-4, ftol = 1e-4, epsmch = 2.220446049250313e-16;
     const double tol = (ftol / epsmch) * epsmch;
     const int maxls = 20, maxiter = 15000, maxfun = 15000;
-    double x = mine ? x0l : 0.0, g, d, t, r, xlast;
-    double f, fold, theta = 1.0;
-    int col = 0, head = 0, nit = 0, nfev = 0, st = 0;
+    double x = mine ? x0l : 0.0, g = 0.0, d = 0.0, t = 0.0, r = 0.0, xlast = 0.0;
+    double f = 0.0, fold = 0.0, theta = 1.0, stp = 0.0, gd = 0.0, gdold = 0.0;
+    int col = 0, head = 0, nit = 0, nfev = 0, st = 0, ifun = 0;
+    bool first = true;
+    Dcsrch ls;
     o.ns = o.nv = o.nc = 0;
-    EvalOut ev;
-    eval_fg(P, map, m, M, lane, x, true, ev);
-    o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
-    if (ev.status) { o.status = ev.status; o.nit = 0; o.nfev = 0; o.x = x; return; }
-    f = ev.f; g = mine ? ev.g : 0.0; nfev = 1; xlast = x;
-#pragma unroll
-    for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
-    if (warp_max(fabs(g)) <= pgtol) { st = 1; goto done; }
     for (;;) {
-        // ---- d = -H g -----------------------------------------------------------------------------
-        {
-            double q = g;
-            double al[HIST];
+        // ---- the evaluation site: f, g at x (skipped when x is bit-identical to the last evaluated point) ------
+        const bool same = !first && __all_sync(FULL, !mine || x == xlast);
+        if (!same) {
+            EvalOut ev;
+            eval_fg(P, map, m, M, lane, x, true, ev);
+            o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
+            if (ev.status) { o.status = ev.status; o.nit = nit; o.nfev = nfev; o.x = x; return; }
+            f = ev.f; g = mine ? ev.g : 0.0; nfev++; xlast = x;
 #pragma unroll
-            for (int k = HIST - 1; k >= 0; k--) {
-                if (k < col) {
-                    const int j = (head + k) % HIST;
-                    const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
-                    al[k] = m.rho[j] * warp_sum(sj * q);
-                    q -= al[k] * yj;
-                }
-            }
-            if (theta != 1.0) q /= theta;
-#pragma unroll
-            for (int k = 0; k < HIST; k++) {
-                if (k < col) {
-                    const int j = (head + k) % HIST;
-                    const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
-                    const double b = m.rho[j] * warp_sum(yj * q);
-                    q += (al[k] - b) * sj;
-                }
-            }
-            d = -q;
+            for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
         }
-        // ---- line search (lnsrlb + dcsrch) ----------------------------------------------------------
-        const double dnorm = sqrt(warp_sum(d * d));
-        double stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
-        t = x; r = g; fold = f;
-        double gd = warp_sum(g * d);
-        const double gdold = gd;
-        bool fail = false;
-        if (gd >= 0.0) fail = true;
-        else {
-            Dcsrch ls;
-            dcsrch_start(ls, stp, f, gd);
-            int ifun = 0;
-            for (;;) {
-                ifun++;
-                if (ifun - 1 >= maxls) { fail = true; break; }
-                const double xn = (stp == 1.0) ? (t + d) : (stp * d + t);
-                const bool same = __all_sync(FULL, !mine || xn == xlast);
-                x = xn;
-                if (!same) {
-                    eval_fg(P, map, m, M, lane, x, true, ev);
-                    o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
-                    if (ev.status) { o.status = ev.status; o.nit = nit; o.nfev = nfev; o.x = x; return; }
-                    f = ev.f; g = mine ? ev.g : 0.0; nfev++; xlast = x;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
+        bool new_dir;
+        if (first) {
+            first = false;
+            if (warp_max(fabs(g)) <= pgtol) { st = 1; break; }
+            new_dir = true;
+        } else {
+            gd = warp_sum(g * d);
+            if (dcsrch_step(ls, stp, f, gd) == 0) new_dir = false;        // FG: another trial point
+            else {
+                // ---- the line search accepted the last evaluated point ---------------------------------------
+                nit++;
+                if (warp_max(fabs(g)) <= pgtol) { st = 1; break; }
+                if (fold - f <= tol * max3(fabs(fold), fabs(f), 1.0)) { st = 0; break; }
+                if (nit >= maxiter || nfev > maxfun) { st = 3; break; }
+                const double y = g - r;                                     // matupd
+                const double rr = warp_sum(y * y);
+                double dr, ddum, s;
+                if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; s = d; }
+                else { dr = (gd - gdold) * stp; s = d * stp; ddum = -gdold * stp; }
+                if (!(dr <= epsmch * ddum)) {
+                    int slot;
+                    if (col < HIST) { slot = (head + col) % HIST; col++; }
+                    else { slot = head; head = (head + 1) % HIST; }
+                    if (mine) { m.S[slot * n + lane] = s; m.Y[slot * n + lane] = y; }
+                    if (lane == 0) m.rho[slot] = 1.0 / dr;
+                    theta = rr / dr;
+                    __syncwarp();
                 }
+                new_dir = true;
+            }
+        }
+        for (;;) {      // (re)start a line search; loops only when a failed search drops the memory
+            if (new_dir) {
+                // ---- d = -H g (two-loop recursion, H0 = I/theta) --------------------------------------------
+                double q = g;
+                double al[HIST];
+#pragma unroll
+                for (int k = HIST - 1; k >= 0; k--) {
+                    if (k < col) {
+                        const int j = (head + k) % HIST;
+                        const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
+                        al[k] = m.rho[j] * warp_sum(sj * q);
+                        q -= al[k] * yj;
+                    }
+                }
+                if (theta != 1.0) q /= theta;
+#pragma unroll
+                for (int k = 0; k < HIST; k++) {
+                    if (k < col) {
+                        const int j = (head + k) % HIST;
+                        const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
+                        const double b = m.rho[j] * warp_sum(yj * q);
+                        q += (al[k] - b) * sj;
+                    }
+                }
+                d = -q;
+                // ---- lnsrlb: set up the search -----------------------------------------------------------------
+                const double dnorm = sqrt(warp_sum(d * d));
+                stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
+                t = x; r = g; fold = f;
                 gd = warp_sum(g * d);
-                if (dcsrch_step(ls, stp, f, gd)) break;
+                gdold = gd;
+                ifun = 0;
+                if (gd >= 0.0) ifun = maxls + 1;                            // not a descent direction: fail
+                else dcsrch_start(ls, stp, f, gd);
             }
-        }
-        if (fail) {
+            ifun++;
+            if (ifun - 1 < maxls) break;                                    // evaluate the trial point
+            // ---- failed search: restore the iterate; ABNORMAL if the memory is already empty ------------------
             x = t; g = r; f = fold;
             if (col == 0) { st = 2; goto done; }
             col = 0; head = 0; theta = 1.0;
-            continue;
+            new_dir = true;
         }
-        nit++;
-        if (warp_max(fabs(g)) <= pgtol) { st = 1; goto done; }
-        if (fold - f <= tol * max3(fabs(fold), fabs(f), 1.0)) { st = 0; goto done; }
-        if (nit >= maxiter || nfev > maxfun) { st = 3; goto done; }
-        // ---- update the memory (matupd) --------------------------------------------------------------
-        {
-            const double y = g - r;
-            const double rr = warp_sum(y * y);
-            double dr, ddum, s;
-            if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; s = d; }
-            else { dr = (gd - gdold) * stp; s = d * stp; ddum = -gdold * stp; }
-            if (dr <= epsmch * ddum) continue;
-            int slot;
-            if (col < HIST) { slot = (head + col) % HIST; col++; }
-            else { slot = head; head = (head + 1) % HIST; }
-            if (mine) { m.S[slot * n + lane] = s; m.Y[slot * n + lane] = y; }
-            if (lane == 0) m.rho[slot] = 1.0 / dr;
-            theta = rr / dr;
-            __syncwarp();
-        }
+        x = (stp == 1.0) ? (t + d) : (stp * d + t);
     }
 done:
     o.x = x; o.status = st; o.nit = nit; o.nfev = nfev;

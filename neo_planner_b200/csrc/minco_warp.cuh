@@ -66,6 +66,7 @@ struct WarpMem {
     double *h;     // [M][12]  dW/d(boundary state): (ps, vs, as, pe, ve, ae) x (x, y)
     double *Gs;    // [M+1][10] per interior node: (Gq+Gp, Gv, Ga, lamJ, lamS) x (x, y)
     double *e0;    // [2M]     energy per (piece, dim)
+    double *nsd;   // [M][2]   sample count of the piece (as double) and its reciprocal
     double *gout;  // [n]      gradient staging
     double *ht;    // [12]     head (3,2), tail (3,2)
     double *S;     // [HIST][n]
@@ -77,7 +78,7 @@ __host__ __device__ inline int warp_mem_doubles(int M)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + n + 12 + 2 * HIST * n + HIST;
+              2 * M + 2 * M + n + 12 + 2 * HIST * n + HIST;
     return (tot + 1) & ~1;
 }
 
@@ -99,6 +100,7 @@ __device__ inline WarpMem carve(double *base, int M)
     m.h = base; base += 12 * M;
     m.Gs = base; base += 10 * M1;
     m.e0 = base; base += 2 * M;
+    m.nsd = base; base += 2 * M;
     m.gout = base; base += n;
     m.ht = base; base += 12;
     m.S = base; base += HIST * n;
@@ -297,6 +299,9 @@ __device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem 
         const double a = 1.0 / T, a2 = a * a;
         double *it = m.iT + 5 * lane;
         it[0] = a; it[1] = a2; it[2] = a2 * a; it[3] = a2 * a2; it[4] = a2 * a2 * a;
+        const int ns = (int)(T / P.dt);                       // sample_num = int(T/delta_t) (EP:401)
+        m.nsd[2 * lane] = (double)ns;
+        m.nsd[2 * lane + 1] = 1.0 / (double)ns;
     }
     e_out = e;
     bad = __reduce_max_sync(FULL, bad);
@@ -348,9 +353,8 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     // ---- sampled penalties (EP:392-466): lanes over the samples of one piece at a time ---------------
     double costs2 = 0.0, costs3 = 0.0;
     for (int i = 0; i < M; i++) {
-        const double Ti = m.ts[i];
-        const int ns = (int)(Ti / P.dt);                    // int(T/delta_t) (EP:401)
-        const double inv_ns = 1.0 / (double)ns;
+        const int ns = (int)m.nsd[2 * i];                    // int(T/delta_t) (EP:401)
+        const double inv_ns = m.nsd[2 * i + 1];
         const double *ci = m.c + 12 * i;
         double cx[6], cy[6];
 #pragma unroll
@@ -373,10 +377,13 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
             // reference's.
             const double dy = py - map.oy, dx = px - map.ox;
             double fr = dy * map.inv_res, fc = dx * map.inv_res;
-            if (fabs(fr - rint(fr)) < 1e-9 * fmax(1.0, fabs(fr))) fr = dy / map.res;
-            if (fabs(fc - rint(fc)) < 1e-9 * fmax(1.0, fabs(fc))) fc = dx / map.res;
+            double tr = trunc(fr), tc = trunc(fc);
+            {   // |estimate - exact quotient| <= 4.5e-16 |q| < 1e-9 for every in-map index (|q| < 2^20)
+                const double er = fabs(fr - tr), ec = fabs(fc - tc);
+                if (er < 1e-9 || er > 1.0 - 1e-9) { fr = dy / map.res; tr = trunc(fr); }
+                if (ec < 1e-9 || ec > 1.0 - 1e-9) { fc = dx / map.res; tc = trunc(fc); }
+            }
             if (fr != fr || fc != fc) bad = 6;                 // int(nan) raises ValueError
-            const double tr = trunc(fr), tc = trunc(fc);
             const bool inside = tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W;
             double dis = 10000.0;
             const Cell *cell = map.cells;
