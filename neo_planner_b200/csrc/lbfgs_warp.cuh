@@ -144,8 +144,12 @@ struct OptOut {
 
 // plan_once's minimize() (EP:213-225). x0l: lane l < n holds x0[l].
 // Written as a state machine around ONE evaluation site so the (large) fused evaluator is instantiated once.
+// cancel_word/cancel_mask: when (*cancel_word & cancel_mask) becomes non-zero (an earlier attempt of the same problem
+// has been accepted, so this speculative attempt can never be the returned one) the run stops with ST_CANCELLED.
+constexpr int ST_CANCELLED = 7;
 __device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
-                                   double x0l, OptOut &o)
+                                   double x0l, OptOut &o, const unsigned *cancel_word = nullptr,
+                                   unsigned cancel_mask = 0u)
 {
     const int n = 3 * M - 2;
     const bool mine = lane < n;
@@ -181,6 +185,9 @@ __device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const
             else {
                 // ---- the line search accepted the last evaluated point ---------------------------------------
                 nit++;
+                if (cancel_mask && (*reinterpret_cast<const volatile unsigned *>(cancel_word) & cancel_mask)) {
+                    st = ST_CANCELLED; break;
+                }
                 if (warp_max(fabs(g)) <= pgtol) { st = 1; break; }
                 if (fold - f <= tol * max3(fabs(fold), fabs(f), 1.0)) { st = 0; break; }
                 if (nit >= maxiter || nfev > maxfun) { st = 3; break; }

@@ -34,56 +34,109 @@ struct OptArgs {
     int retry_status;            // NEO_ST_DOMAIN if retry_ts is outside (T_min, T_max)
     const MapView *maps;
     unsigned int *counter;       // work queue head
+    // per-task records (task = attempt * B + problem), written by the warp that ran the attempt
+    double *t_x;                 // (A*B, n)
+    double *t_costs;             // (A*B, 4)
+    int32_t *t_info;             // (A*B, 4): status, nit, nfev, completed (minimize() returned)
+    long long *t_work;           // (A*B, 3)
+    unsigned int *p_state;       // (B): bits 0..7 attempts finished, bits 8..15 attempts accepted
     double *x, *ts, *coeffs, *costs;
     int32_t *status, *ok, *attempt, *nit, *runs, *nfev;
     long long *work;
 };
 
-// Persistent warps: each warp pulls problems from a global queue (evaluation counts vary 10..400 per problem)
-// and runs warm_start_plan (EP:186-203) for it entirely on chip.
+// A problem is resolved once its lowest accepted attempt has all earlier attempts finished, or all attempts finished.
+__device__ __forceinline__ bool resolved(unsigned st, int A)
+{
+    const unsigned done = st & 0xffu, okm = (st >> 8) & 0xffu;
+    if (okm) { const unsigned lower = (1u << (__ffs(okm) - 1)) - 1u; return (done & lower) == lower; }
+    return done == (1u << A) - 1u;
+}
+
+// Persistent warps pull TASKS = (attempt, problem) from a global queue in attempt-major order and run one
+// plan_once (EP:205-237) per task entirely on chip. warm_start_plan (EP:186-203) semantics are kept exactly -- the
+// returned attempt is the lowest-index accepted one and counters are summed over attempts 0..that one -- but a retry
+// whose predecessor is still running on another warp is started SPECULATIVELY on an otherwise idle warp (its inputs,
+// straight line + host-drawn noise, do not depend on the predecessor). A speculative attempt is skipped or cancelled
+// as soon as an earlier attempt of its problem is accepted. With many problems per SM the queue reaches the retries
+// only when first attempts are finished, so speculation costs nothing; with few problems it halves the tail.
+// The warp whose completion resolves a problem assembles its outputs (final coefficients included).
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int M = a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M;
+    const int M = a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M, A = a.max_attempts;
     const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
+    const unsigned total = (unsigned)A * (unsigned)a.B;
     for (;;) {
-        unsigned int idx = 0;
-        if (lane == 0) idx = atomicAdd(a.counter, 1u);
-        idx = __shfl_sync(FULL, idx, 0);
-        if (idx >= (unsigned)a.B) break;
-        const size_t b = idx;
-        if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
-        const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-        __syncwarp();
-        int status = 0, ok = 0, attempt = 0, nit = 0, runs = 0, nfev = 0;
-        unsigned long long ns = 0, nv = 0, nc = 0;
-        double xf = 0.0, costs[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int at = 0; at < a.max_attempts; at++) {
-            attempt = at;
+        unsigned int tid = 0;
+        if (lane == 0) tid = atomicAdd(a.counter, 1u);
+        tid = __shfl_sync(FULL, tid, 0);
+        if (tid >= total) break;
+        const int at = (int)(tid / (unsigned)a.B);
+        const size_t b = tid - (unsigned)at * (unsigned)a.B;
+        const unsigned lower_ok = ((1u << at) - 1u) << 8;
+        unsigned bits = 1u << at;
+        const unsigned seen = *reinterpret_cast<volatile unsigned *>(a.p_state + b);
+        if (!(seen & lower_ok)) {
+            if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
+            const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
+            __syncwarp();
             double x0l = 0.0;
             int st0 = 0;
             if (at == 0) {
                 if (lane < n) x0l = a.x0[b * n + lane];
                 st0 = a.x0_status ? a.x0_status[b] : 0;
             } else {
-                if (lane < nq) x0l = a.retry_q[(b * (a.max_attempts - 1) + (at - 1)) * nq + lane];
+                if (lane < nq) x0l = a.retry_q[(b * (A - 1) + (at - 1)) * nq + lane];
                 else if (lane < n) x0l = a.retry_tau[lane - nq];
                 st0 = a.retry_status;
             }
-            if (st0) { status = st0; continue; }           // map_T2tau raised (EP:209): attempt lost
             OptOut o;
-            lbfgsb_warp(P, map, m, M, lane, x0l, o);
-            nfev += o.nfev; ns += o.ns; nv += o.nv; nc += o.nc;
-            status = o.status;
-            if (o.status >= NEO_ST_OVERFLOW) continue;     // exception propagated out of minimize()
-            runs++; nit += o.nit; xf = o.x;
-#pragma unroll
-            for (int k = 0; k < 4; k++) costs[k] = o.costs[k];
-            if (!(costs[3] * P.w3 > P.collision_cost_tol)) { ok = 1; break; }   // EP:235-237
+            o.status = st0; o.nit = 0; o.nfev = 0; o.ns = o.nv = o.nc = 0; o.x = 0.0;
+            o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
+            if (!st0) lbfgsb_warp(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok);   // else map_T2tau raised (EP:209)
+            if (o.status != ST_CANCELLED) {
+                const bool completed = o.status < NEO_ST_OVERFLOW;             // minimize() returned (EP:213-233)
+                const bool accepted = completed && !(o.costs[3] * P.w3 > P.collision_cost_tol);   // EP:235-237
+                if (lane < n) a.t_x[(size_t)tid * n + lane] = o.x;
+                if (lane < 4) a.t_costs[(size_t)tid * 4 + lane] = o.costs[lane];
+                if (lane == 0) {
+                    a.t_info[(size_t)tid * 4 + 0] = o.status; a.t_info[(size_t)tid * 4 + 1] = o.nit;
+                    a.t_info[(size_t)tid * 4 + 2] = o.nfev; a.t_info[(size_t)tid * 4 + 3] = completed ? 1 : 0;
+                    a.t_work[(size_t)tid * 3 + 0] = (long long)o.ns; a.t_work[(size_t)tid * 3 + 1] = (long long)o.nv;
+                    a.t_work[(size_t)tid * 3 + 2] = (long long)o.nc;
+                }
+                if (accepted) bits |= 1u << (8 + at);
+                __threadfence();
+            }
         }
-        // final (int_wpts, ts) -> ts, coefficients (EP:226-229, TU:182)
-        if (runs > 0) {
+        __syncwarp();
+        unsigned old = 0;
+        if (lane == 0) old = atomicOr(a.p_state + b, bits);
+        old = __shfl_sync(FULL, old, 0);
+        const unsigned now = old | bits;
+        if (!resolved(now, A) || resolved(old, A)) continue;
+
+        // ---- this warp resolved problem b: assemble warm_start_plan's outputs ---------------------------------
+        __threadfence();
+        const unsigned okm = (now >> 8) & 0xffu;
+        const int last = okm ? __ffs(okm) - 1 : A - 1;      // returned attempt (EP:196-203)
+        int nit = 0, runs = 0, nfev = 0, src = -1, status = 0;
+        long long ns = 0, nv = 0, nc = 0;
+        for (int k = 0; k <= last; k++) {
+            const size_t t = (size_t)k * a.B + b;
+            const int st = __ldcg(a.t_info + t * 4 + 0);
+            status = st;
+            nfev += __ldcg(a.t_info + t * 4 + 2);
+            ns += __ldcg(a.t_work + t * 3 + 0); nv += __ldcg(a.t_work + t * 3 + 1); nc += __ldcg(a.t_work + t * 3 + 2);
+            if (__ldcg(a.t_info + t * 4 + 3)) { runs++; nit += __ldcg(a.t_info + t * 4 + 1); src = k; }
+        }
+        if (src >= 0) {      // final (int_wpts, ts) -> ts, coefficients (EP:226-229, TU:182)
+            const size_t t = (size_t)src * a.B + b;
+            const double xf = lane < n ? __ldcg(a.t_x + t * n + lane) : 0.0;
+            if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
+            __syncwarp();
             double e_unused;
             times_from_tau(P, m, M, lane, xf, e_unused);
             load_nodes(m, M, lane, xf);
@@ -92,16 +145,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_optimize(const DevParams
             if (lane < n) a.x[b * n + lane] = xf;
             if (lane < M) a.ts[b * M + lane] = m.ts[lane];
             for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = m.c[i];
+            if (lane < 4) a.costs[b * 4 + lane] = __ldcg(a.t_costs + t * 4 + lane);
         } else {
             if (lane < n) a.x[b * n + lane] = 0.0;
             if (lane < M) a.ts[b * M + lane] = 0.0;
             for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = 0.0;
+            if (lane < 4) a.costs[b * 4 + lane] = 0.0;
         }
-        if (lane < 4) a.costs[b * 4 + lane] = costs[lane];
         if (lane == 0) {
-            a.status[b] = status; a.ok[b] = ok; a.attempt[b] = attempt; a.nit[b] = nit; a.runs[b] = runs;
+            a.status[b] = status; a.ok[b] = okm ? 1 : 0; a.attempt[b] = last; a.nit[b] = nit; a.runs[b] = runs;
             a.nfev[b] = nfev;
-            if (a.work) { a.work[b * 3] = (long long)ns; a.work[b * 3 + 1] = (long long)nv; a.work[b * 3 + 2] = (long long)nc; }
+            if (a.work) { a.work[b * 3] = ns; a.work[b * 3 + 1] = nv; a.work[b * 3 + 2] = nc; }
         }
         __syncwarp();
     }
@@ -524,11 +578,21 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     int occ;
     int rc = prep_kernel(h, k_optimize, a.M, &occ);
     if (rc) return rc;
-    const int need = (a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
+    const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
+    const size_t need = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int grid = (int)(need < (size_t)occ * h->sm_count ? need : (size_t)occ * h->sm_count);
+    // per-task scratch records + per-problem state word (library-owned, grow-only)
+    char *base;
+    const size_t o_x = 0, o_c = o_x + sizeof(double) * tasks * n, o_w = o_c + sizeof(double) * tasks * 4,
+                 o_i = o_w + sizeof(long long) * tasks * 3, o_p = o_i + sizeof(int32_t) * tasks * 4,
+                 total = o_p + sizeof(unsigned) * a.B;
+    if ((rc = dev_buf(h, 6, total, (void **)&base))) return rc;
+    a.t_x = (double *)(base + o_x); a.t_costs = (double *)(base + o_c); a.t_work = (long long *)(base + o_w);
+    a.t_info = (int32_t *)(base + o_i); a.p_state = (unsigned *)(base + o_p);
     a.maps = h->d_maps;
     a.counter = h->d_counter;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
     k_optimize<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
