@@ -147,7 +147,7 @@ struct OptOut {
 // cancel_word/cancel_mask: when (*cancel_word & cancel_mask) becomes non-zero (an earlier attempt of the same problem
 // has been accepted, so this speculative attempt can never be the returned one) the run stops with ST_CANCELLED.
 constexpr int ST_CANCELLED = 7;
-__device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
+__device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
                                    double x0l, OptOut &o, const unsigned *cancel_word = nullptr,
                                    unsigned cancel_mask = 0u)
 {
@@ -212,25 +212,22 @@ __device__ inline void lbfgsb_warp(const DevParams &P, const MapView &map, const
             if (new_dir) {
                 // ---- d = -H g (two-loop recursion, H0 = I/theta) --------------------------------------------
                 double q = g;
-                double al[HIST];
-#pragma unroll
-                for (int k = HIST - 1; k >= 0; k--) {
-                    if (k < col) {
-                        const int j = (head + k) % HIST;
-                        const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
-                        al[k] = m.rho[j] * warp_sum(sj * q);
-                        q -= al[k] * yj;
-                    }
+#pragma unroll 1
+                for (int k = col - 1; k >= 0; k--) {
+                    const int j = (head + k) % HIST;
+                    const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
+                    const double al = m.rho[j] * warp_sum(sj * q);
+                    if (lane == 0) m.al[k] = al;
+                    q -= al * yj;
                 }
                 if (theta != 1.0) q /= theta;
-#pragma unroll
-                for (int k = 0; k < HIST; k++) {
-                    if (k < col) {
-                        const int j = (head + k) % HIST;
-                        const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
-                        const double b = m.rho[j] * warp_sum(yj * q);
-                        q += (al[k] - b) * sj;
-                    }
+                __syncwarp();
+#pragma unroll 1
+                for (int k = 0; k < col; k++) {
+                    const int j = (head + k) % HIST;
+                    const double sj = mine ? m.S[j * n + lane] : 0.0, yj = mine ? m.Y[j * n + lane] : 0.0;
+                    const double b = m.rho[j] * warp_sum(yj * q);
+                    q += (m.al[k] - b) * sj;
                 }
                 d = -q;
                 // ---- lnsrlb: set up the search -----------------------------------------------------------------

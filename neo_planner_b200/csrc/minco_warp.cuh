@@ -72,13 +72,14 @@ struct WarpMem {
     double *S;     // [HIST][n]
     double *Y;     // [HIST][n]
     double *rho;   // [HIST]
+    double *al;    // [HIST]   two-loop recursion coefficients
 };
 
 __host__ __device__ inline int warp_mem_doubles(int M)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * HIST * n + HIST;
+              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST;
     return (tot + 1) & ~1;
 }
 
@@ -105,7 +106,8 @@ __device__ inline WarpMem carve(double *base, int M)
     m.ht = base; base += 12;
     m.S = base; base += HIST * n;
     m.Y = base; base += HIST * n;
-    m.rho = base;
+    m.rho = base; base += HIST;
+    m.al = base;
     return m;
 }
 

@@ -22,6 +22,9 @@ using namespace neo;
 // kernels
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
+#ifndef NEO_MIN_CTAS
+#define NEO_MIN_CTAS 2
+#endif
 
 struct OptArgs {
     int B, M, max_attempts;
@@ -61,7 +64,7 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // as soon as an earlier attempt of its problem is accepted. With many problems per SM the queue reaches the retries
 // only when first attempts are finished, so speculation costs nothing; with few problems it halves the tail.
 // The warp whose completion resolves a problem assembles its outputs (final coefficients included).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_optimize(const DevParams P, const OptArgs a)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, 'libneoopt.so')
+SO = os.environ.get('NEO_SO') or os.path.join(HERE, 'libneoopt.so')     # NEO_SO: development override
 
 MAX_PIECES = 10
 MAX_ATTEMPTS = 8
