@@ -1,0 +1,108 @@
+"""Multi-GPU sharding of independent planning problems: one process per GPU, problems partitioned
+across ranks with no data-path collective, and ONE all-gather of fixed-size result records at the end of a batch
+(torch.distributed; NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests). The reference has no distributed
+code; this is the B200-native way to run its expert data-generation sweep (config 4) on an 8-GPU box."""
+from __future__ import annotations
+
+import numpy as np
+
+INT_FIELDS = ('status', 'ok', 'attempt', 'nit', 'runs', 'nfev')
+
+
+def shard_worlds(n_worlds: int, world_size: int, rank: int):
+    """Contiguous block of world ids owned by `rank` (each GPU uploads only its own maps)."""
+    per, extra = divmod(n_worlds, world_size)
+    start = rank * per + min(rank, extra)
+    return list(range(start, start + per + (1 if rank < extra else 0)))
+
+
+def shard_problems(world_of_problem, world_size: int, rank: int):
+    """Indices of the problems whose world belongs to `rank` under shard_worlds."""
+    world_of_problem = np.asarray(world_of_problem)
+    n_worlds = int(world_of_problem.max()) + 1 if world_of_problem.size else 0
+    mine = np.zeros(max(n_worlds, 1), dtype=bool)
+    mine[shard_worlds(n_worlds, world_size, rank)] = True
+    return np.nonzero(mine[world_of_problem])[0]
+
+
+def record_width(M: int) -> int:
+    return (3 * M - 2) + M + 12 * M + 4 + len(INT_FIELDS)
+
+
+def pack_records(res, M: int) -> np.ndarray:
+    """dict of result arrays (neo_result) -> (B, record_width) float64 (integers are exact in fp64)."""
+    B = res['x'].shape[0]
+    parts = [res['x'].reshape(B, -1), res['ts'].reshape(B, -1), res['coeffs'].reshape(B, -1), res['costs'].reshape(B, -1)]
+    parts += [res[k].reshape(B, 1).astype(np.float64) for k in INT_FIELDS]
+    rec = np.concatenate(parts, axis=1)
+    assert rec.shape[1] == record_width(M)
+    return np.ascontiguousarray(rec)
+
+
+def unpack_records(rec: np.ndarray, M: int):
+    n = 3 * M - 2
+    B = rec.shape[0]
+    out, o = {}, 0
+    for key, w, shape in (('x', n, (B, n)), ('ts', M, (B, M)), ('coeffs', 12 * M, (B, 6 * M, 2)), ('costs', 4, (B, 4))):
+        out[key] = rec[:, o:o + w].reshape(shape).copy(); o += w
+    for key in INT_FIELDS:
+        out[key] = rec[:, o].astype(np.int32); o += 1
+    return out
+
+
+def gather_records(local_rec: np.ndarray, local_idx: np.ndarray, total: int, device=None):
+    """All-gather the per-rank records into global problem order on every rank. Ranks may own different counts:
+    records are padded to the maximum count (one collective of fixed size, then the padding is dropped)."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size()
+    width = local_rec.shape[1]
+    counts = [None] * ws
+    dist.all_gather_object(counts, int(local_rec.shape[0]))
+    cap = max(counts)
+    dev = torch.device('cpu') if device is None else device
+    buf = torch.zeros((cap, width + 1), dtype=torch.float64, device=dev)
+    if local_rec.shape[0]:
+        buf[:local_rec.shape[0], :width] = torch.from_numpy(local_rec).to(dev)
+        buf[:local_rec.shape[0], width] = torch.from_numpy(np.asarray(local_idx, dtype=np.float64)).to(dev)
+    allbuf = torch.zeros((ws * cap, width + 1), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allbuf, buf)
+    allbuf = allbuf.cpu().numpy().reshape(ws, cap, width + 1)
+    out = np.zeros((total, width))
+    seen = np.zeros(total, dtype=bool)
+    for r in range(ws):
+        rows = allbuf[r, :counts[r]]
+        idx = rows[:, width].astype(np.int64)
+        out[idx] = rows[:, :width]
+        seen[idx] = True
+    if not seen.all():
+        raise RuntimeError(f'{int((~seen).sum())} problems were not solved by any rank')
+    return out
+
+
+class ShardedPlanner:
+    """Runs `solve(head, tail, local_map_ids) -> result dict` on this rank's share of a global problem list and returns
+    the gathered results (global order) on every rank. `solve` is normally BatchPlanner.plan bound to this rank's GPU;
+    the CPU tests pass a stand-in so the partition/gather logic is covered without a device."""
+
+    def __init__(self, solve, M: int, rank: int, world_size: int, device=None):
+        self.solve, self.M, self.rank, self.world_size, self.device = solve, M, rank, world_size, device
+
+    def local_worlds(self, n_worlds):
+        return shard_worlds(n_worlds, self.world_size, self.rank)
+
+    def plan(self, head, tail, world_of_problem):
+        head = np.asarray(head); tail = np.asarray(tail); world_of_problem = np.asarray(world_of_problem)
+        idx = shard_problems(world_of_problem, self.world_size, self.rank)
+        n_worlds = int(world_of_problem.max()) + 1
+        first = self.local_worlds(n_worlds)[0] if len(idx) else 0
+        if len(idx):
+            res = self.solve(head[idx], tail[idx], (world_of_problem[idx] - first).astype(np.int32))
+            rec = pack_records(res, self.M)
+        else:
+            rec = np.zeros((0, record_width(self.M)))
+        if self.world_size == 1:
+            full = np.zeros((len(head), rec.shape[1])); full[idx] = rec
+        else:
+            full = gather_records(rec, idx, len(head), self.device)
+        return unpack_records(full, self.M)
