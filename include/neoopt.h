@@ -79,6 +79,14 @@ int neo_set_map_esdf(neo_handle *h, int slot, int H, int W, double res, double o
  * Bit-exact with scipy.ndimage.distance_transform_edt + numpy.gradient. */
 int neo_set_map_occupancy(neo_handle *h, int slot, int H, int W, double res, double ox, double oy,
                           const int8_t *occ);
+/* Map build from a point cloud / voxel-centre list (the step before ESDF.occupancy_map_cb, done by the external
+ * octomap_server in the reference: map_server_global.launch:17-31): xyz (n,3) float32 as stored in a .pcd; a cell
+ * (row = floor((y-oy)/res), col = floor((x-ox)/res)) is occupied iff a point with z_min <= z <= z_max falls into it;
+ * then the same exact EDT + gradient as neo_set_map_occupancy. */
+int neo_set_map_points(neo_handle *h, int slot, int n_points, const float *xyz, double z_min, double z_max,
+                       int H, int W, double res, double ox, double oy);
+/* The binarised (0 / 100) grid the last neo_set_map_occupancy / neo_set_map_points call on this slot used: occ (H, W). */
+int neo_get_occupancy(neo_handle *h, int slot, int8_t *occ);
 /* Read a slot back (for checks / for filling a reference ESDF object): each out array (H, W) or NULL. */
 int neo_get_map(neo_handle *h, int slot, double *esdf, double *gx, double *gy);
 /* ESDF.get_edt_dis / get_edt_grad (ESDF:53-82) for n points xy (n,2): idx (n,2) = row, col (-1,-1 when

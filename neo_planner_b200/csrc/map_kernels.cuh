@@ -12,6 +12,20 @@ namespace neo {
 
 constexpr int EDT_INF = 1 << 28;
 
+// Point cloud / voxel-centre list -> 2-D occupancy: a cell is occupied (100) iff at least one point with
+// z_min <= z <= z_max falls into its column (what octomap_server's projected_map delivers to ESDF.occupancy_map_cb for
+// the slab [occupancy_min_z, occupancy_max_z], map_server_global.launch:26-31). xyz: (n,3) float32 as stored in .pcd.
+__global__ void k_points_to_occ(const float *__restrict__ xyz, int n, double z_min, double z_max, double ox, double oy,
+                                double res, int H, int W, int8_t *__restrict__ occ)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = (double)xyz[3 * i], y = (double)xyz[3 * i + 1], z = (double)xyz[3 * i + 2];
+    if (!(z >= z_min && z <= z_max)) return;
+    const double fc = floor(__ddiv_rn(__dsub_rn(x, ox), res)), fr = floor(__ddiv_rn(__dsub_rn(y, oy), res));
+    if (fr >= 0.0 && fr < (double)H && fc >= 0.0 && fc < (double)W) occ[(size_t)(int)fr * W + (int)fc] = 100;
+}
+
 // pass 1: one thread per row; g[r][c] = squared distance to the nearest occupied cell of row r (EDT_INF if none)
 __global__ void k_edt_rows(const int8_t *__restrict__ occ, int H, int W, int *__restrict__ g, int *__restrict__ any)
 {

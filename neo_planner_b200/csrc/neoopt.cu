@@ -280,6 +280,8 @@ __global__ void k_exp_dd(int n, const double *x, double *y)
 // ---------------------------------------------------------------------------------------------------------
 struct MapSlot {
     Cell *cells = nullptr;
+    int8_t *occ = nullptr;       // binarised grid of the last occupancy / point-cloud build
+    size_t occ_cap = 0;
     int H = 0, W = 0;
     double res = 0, ox = 0, oy = 0;
 };
@@ -394,7 +396,7 @@ extern "C" int neo_destroy(neo_handle *h)
     if (!h) return NEO_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (auto &s : h->slots) if (s.cells) cudaFree(s.cells);
+    for (auto &s : h->slots) { if (s.cells) cudaFree(s.cells); if (s.occ) cudaFree(s.occ); }
     for (auto &b : h->bufs) if (b.p) cudaFree(b.p);
     cudaFree(h->d_maps); cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -470,6 +472,38 @@ extern "C" int neo_set_map_esdf(neo_handle *h, int slot, int H, int W, double re
     return slot_publish(h, slot);
 }
 
+// occupancy (device, int8) -> exact EDT -> cells; d_occ lives in staging buffer 0 (offset 0)
+static int build_from_occ(neo_handle *h, int slot, int H, int W, double res, char *base, size_t off_g, size_t off_any, size_t off_e)
+{
+    const int8_t *d_occ = (const int8_t *)base;
+    int *d_g = (int *)(base + off_g), *d_any = (int *)(base + off_any);
+    double *d_e = (double *)(base + off_e);
+    MapSlot &s = h->slots[slot];
+    const size_t n = (size_t)H * W;
+    if (s.occ && s.occ_cap < n) { CK(cudaFree(s.occ)); s.occ = nullptr; }
+    if (!s.occ) { CK(cudaMalloc(&s.occ, n)); s.occ_cap = n; }
+    CK(cudaMemcpyAsync(s.occ, d_occ, n, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemsetAsync(d_any, 0, sizeof(int), h->stream));
+    k_edt_rows<<<(H + 63) / 64, 64, 0, h->stream>>>(d_occ, H, W, d_g, d_any);
+    dim3 grid((W + 127) / 128, H);
+    k_edt_cols<<<grid, 128, 0, h->stream>>>(d_g, H, W, d_any, res, d_e);
+    k_pack_cells<<<grid, 128, 0, h->stream>>>(d_e, nullptr, nullptr, H, W, s.cells, nullptr, nullptr);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return slot_publish(h, slot);
+}
+
+struct OccLayout { size_t off_g, off_any, off_e, total; };
+static OccLayout occ_layout(size_t n)
+{
+    OccLayout L;
+    L.off_g = (n + 255) & ~(size_t)255;
+    L.off_any = L.off_g + sizeof(int) * n;
+    L.off_e = (L.off_any + 256 + 255) & ~(size_t)255;
+    L.total = L.off_e + sizeof(double) * n;
+    return L;
+}
+
 extern "C" int neo_set_map_occupancy(neo_handle *h, int slot, int H, int W, double res, double ox, double oy,
                                      const int8_t *occ)
 {
@@ -481,21 +515,50 @@ extern "C" int neo_set_map_occupancy(neo_handle *h, int slot, int H, int W, doub
     int rc = slot_prepare(h, slot, H, W, res, ox, oy);
     if (rc) return rc;
     const size_t n = (size_t)H * W;
+    const OccLayout L = occ_layout(n);
     char *base;
-    const size_t off_g = (n + 255) & ~(size_t)255, off_any = off_g + sizeof(int) * n, off_e = (off_any + 256 + 255) & ~(size_t)255;
-    if ((rc = dev_buf(h, 0, off_e + sizeof(double) * n, (void **)&base))) return rc;
-    int8_t *d_occ = (int8_t *)base;
-    int *d_g = (int *)(base + off_g), *d_any = (int *)(base + off_any);
-    double *d_e = (double *)(base + off_e);
-    CK(cudaMemcpyAsync(d_occ, occ, n, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(d_any, 0, sizeof(int), h->stream));
-    k_edt_rows<<<(H + 63) / 64, 64, 0, h->stream>>>(d_occ, H, W, d_g, d_any);
-    dim3 grid((W + 127) / 128, H);
-    k_edt_cols<<<grid, 128, 0, h->stream>>>(d_g, H, W, d_any, res, d_e);
-    k_pack_cells<<<grid, 128, 0, h->stream>>>(d_e, nullptr, nullptr, H, W, h->slots[slot].cells, nullptr, nullptr);
-    h->launches += 3;
-    CK(cudaGetLastError());
-    return slot_publish(h, slot);
+    if ((rc = dev_buf(h, 0, L.total, (void **)&base))) return rc;
+    CK(cudaMemcpyAsync(base, occ, n, cudaMemcpyHostToDevice, h->stream));
+    return build_from_occ(h, slot, H, W, res, base, L.off_g, L.off_any, L.off_e);
+}
+
+extern "C" int neo_set_map_points(neo_handle *h, int slot, int n_points, const float *xyz, double z_min, double z_max,
+                                  int H, int W, double res, double ox, double oy)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n_points < 0 || (n_points > 0 && !xyz)) return fail(h, "neo_set_map_points: invalid argument");
+    if ((long long)H * H + (long long)W * W >= (long long)EDT_INF) return fail(h, "map too large for the int32 EDT");
+    CK(cudaSetDevice(h->device));
+    int rc = slot_prepare(h, slot, H, W, res, ox, oy);
+    if (rc) return rc;
+    const size_t n = (size_t)H * W;
+    const OccLayout L = occ_layout(n);
+    char *base;
+    float *d_xyz;
+    if ((rc = dev_buf(h, 0, L.total, (void **)&base))) return rc;
+    if ((rc = dev_buf(h, 1, sizeof(float) * 3 * (size_t)(n_points > 0 ? n_points : 1), (void **)&d_xyz))) return rc;
+    CK(cudaMemsetAsync(base, 0, n, h->stream));
+    if (n_points > 0) {
+        CK(cudaMemcpyAsync(d_xyz, xyz, sizeof(float) * 3 * (size_t)n_points, cudaMemcpyHostToDevice, h->stream));
+        k_points_to_occ<<<(n_points + 255) / 256, 256, 0, h->stream>>>(d_xyz, n_points, z_min, z_max, ox, oy, res, H, W,
+                                                                       (int8_t *)base);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return build_from_occ(h, slot, H, W, res, base, L.off_g, L.off_any, L.off_e);
+}
+
+extern "C" int neo_get_occupancy(neo_handle *h, int slot, int8_t *occ)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (slot < 0 || slot >= (int)h->slots.size() || !h->slots[slot].occ || !occ) return fail(h, "neo_get_occupancy: no occupancy in this slot");
+    CK(cudaSetDevice(h->device));
+    const MapSlot &s = h->slots[slot];
+    CK(cudaMemcpyAsync(occ, s.occ, (size_t)s.H * s.W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NEO_OK;
 }
 
 extern "C" int neo_get_map(neo_handle *h, int slot, double *esdf, double *gx, double *gy)

@@ -43,7 +43,7 @@ class Result(C.Structure):
 
 
 EXPORTS = ['neo_create', 'neo_destroy', 'neo_set_config', 'neo_last_error', 'neo_device_info', 'neo_set_map_esdf',
-           'neo_set_map_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
+           'neo_set_map_occupancy', 'neo_set_map_points', 'neo_get_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
            'neo_optimize_dev', 'neo_T2tau', 'neo_get_coeffs', 'neo_sample', 'neo_last_kernel_ms', 'neo_fp64_peak',
            'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host']
 
@@ -68,6 +68,8 @@ def load():
         lib.neo_set_map_esdf.argtypes = [V, I, I, I, D, D, D, V, V, V]
         lib.neo_set_map_occupancy.argtypes = [V, I, I, I, D, D, D, V]
         lib.neo_get_map.argtypes = [V, I, V, V, V]
+        lib.neo_set_map_points.argtypes = [V, I, I, V, D, D, I, I, D, D, D]
+        lib.neo_get_occupancy.argtypes = [V, I, V]
         lib.neo_query_map.argtypes = [V, I, I, V, V, V, V]
         lib.neo_eval.argtypes = [V, I, I, V, V, V, V, V, V, V, V, V]
         lib.neo_eval_dev.argtypes = [V, I, I, V, V, V, V, V, V, V, V, V, V]
@@ -155,6 +157,15 @@ class Handle:
     def set_map_occupancy(self, slot, H, W, res, ox, oy, occ):
         occ = np.ascontiguousarray(np.asarray(occ).reshape(H, W), dtype=np.int8)
         self._ck(self.lib.neo_set_map_occupancy(self.h, slot, H, W, res, ox, oy, ptr(occ)))
+
+    def set_map_points(self, slot, xyz, z_min, z_max, H, W, res, ox, oy):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        self._ck(self.lib.neo_set_map_points(self.h, slot, xyz.shape[0], ptr(xyz), z_min, z_max, H, W, res, ox, oy))
+
+    def get_occupancy(self, slot, H, W):
+        occ = np.empty((H, W), np.int8)
+        self._ck(self.lib.neo_get_occupancy(self.h, slot, ptr(occ)))
+        return occ
 
     def get_map(self, slot, H, W):
         e = np.empty((H, W)); gx = np.empty((H, W)); gy = np.empty((H, W))
