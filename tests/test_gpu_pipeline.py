@@ -1,0 +1,72 @@
+"""GPU tests of the rows next to the hot path: expert data-generation records and the learned
+initializer feeding warm_start_plan (config 3 plumbing; the reference's trained weights are not in its repository)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from neo_planner_b200 import frames, record
+from neo_planner_b200.planner import BatchPlanner
+from neo_planner_b200.worlds import make_world, make_problems, YamlConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def scene(B, seed=0):
+    rng = np.random.default_rng(seed)
+    w = make_world(7)
+    head, tail = make_problems(w, B)
+    yaw = np.arctan2(head[:, 1, 1], head[:, 1, 0]) + rng.normal(0, 0.1, B)
+    att = np.stack([np.cos(yaw / 2), np.zeros(B), np.zeros(B), np.sin(yaw / 2)], axis=1)
+    gp = np.concatenate([head[:, 0] - 0.5 * head[:, 1], np.full((B, 1), 2.0)], axis=1)      # drone 1 s behind the plan start
+    gv = np.concatenate([head[:, 1], np.zeros((B, 1))], axis=1)
+    lv = frames.rotate_inverse(att, gv)
+    depth = rng.uniform(0.3, 10.0, size=(B, 480, 640)).astype(np.float32)
+    init_pos = np.concatenate([head[:, 0], np.full((B, 1), 2.0)], axis=1)
+    init_vel = gv.copy()
+    return w, head, tail, att, gp, gv, lv, depth, init_pos, init_vel
+
+
+def test_batch_recorder_writes_reference_schema(tmp_path):
+    B = 24
+    w, head, tail, att, gp, gv, lv, depth, init_pos, init_vel = scene(B)
+    bp = BatchPlanner(YamlConfig()); bp.set_map(w)
+    rec = record.BatchRecorder(bp, des_pos_z=2.0, out_dir=str(tmp_path / 'training_data'))
+    df, res = rec.record(depth, lv, att, gp, gv, init_pos, init_vel, tail, rng=np.random.default_rng(1))
+    n_ok = int(res['ok'].sum())
+    assert n_ok >= B // 2 and len(df) == n_ok
+    back = pd.read_csv(rec.csv_path)
+    assert list(back.columns) == record.TABLE_HEADER and len(back) == n_ok
+    keep = np.nonzero(res['ok'] == 1)[0]
+    # the stored body-frame waypoints map back to the optimised map-frame waypoints (nn_planner.py:123-134)
+    out = back.iloc[:, -9:].values.astype(float)
+    iw, ts = frames.wpts_world(att[keep], gp[keep], out)
+    assert np.allclose(iw.reshape(n_ok, -1), res['x'][keep, :4], atol=1e-9) and np.allclose(ts, res['ts'][keep], atol=1e-12)
+    import os
+    pngs = sorted(os.listdir(rec.img_path))
+    assert len(pngs) == n_ok and pngs[0] == back['id'][0][1:] + '.png'
+    from PIL import Image
+    im = np.array(Image.open(os.path.join(rec.img_path, pngs[0])))
+    assert im.shape == (480, 640) and im.dtype == np.uint8
+
+
+def test_learned_initializer_feeds_optimizer():
+    import torch
+    from neo_planner_b200.initializer import NeoBatchPlanner
+    B = 48
+    w, head, tail, att, gp, gv, lv, depth, init_pos, init_vel = scene(B, seed=2)
+    bp = BatchPlanner(YamlConfig()); bp.set_map(w)
+    neo = NeoBatchPlanner(bp, des_pos_z=2.0, device='cuda', dtype=torch.bfloat16)
+    res = neo.enhanced_traj_plan(depth, lv, att, gp, gv, init_pos, init_vel, tail, rng=np.random.default_rng(3))
+    assert res['nn_int_wpts'].shape == (B, 2, 2) and res['nn_ts'].shape == (B, 3)
+    assert res['ok'].mean() > 0.6
+    ok = res['ok'] == 1
+    assert np.max(np.abs(res['coeffs'][ok][:, 0, :] - head[ok][:, 0])) < 1e-9
+    # a random-weight network predicts durations outside (T_min, T_max) for some samples: those lose attempt 0 (EP:209)
+    bad = ((res['nn_ts'] <= 0.5) | (res['nn_ts'] >= 5.0)).any(axis=1)
+    assert (res['attempt'][bad & ok] >= 1).all()
+    # a perfect initializer (the optimum itself) converges in far fewer iterations than the expert guess
+    expert = bp.plan(head, tail, rng=np.random.default_rng(3))
+    good = (expert['ok'] == 1) & (expert['attempt'] == 0)
+    warm = bp.warm_start_plan(head[good], tail[good], expert['x'][good][:, :4].reshape(-1, 2, 2), expert['ts'][good],
+                              rng=np.random.default_rng(3))
+    assert warm['nit'].mean() < 0.5 * expert['nit'][good].mean()

@@ -103,3 +103,74 @@ def test_exp_dd_host_build_is_correctly_rounded():
             T1 = (T_max - T_min) / (1 + e1) + T_min
             T2 = (T_max - T_min) / (1 + math.exp(-tau)) + T_min
             assert T1 == T2, T
+
+
+def test_frames_against_scipy_rotation():
+    from scipy.spatial.transform import Rotation
+    from neo_planner_b200 import frames
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=(50, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)      # (w, x, y, z)
+    v = rng.normal(size=(50, 3))
+    rot = Rotation.from_quat(q[:, [1, 2, 3, 0]])                                      # scipy wants (x, y, z, w)
+    assert np.allclose(frames.rotation_matrix(q), rot.as_matrix(), atol=1e-14)
+    assert np.allclose(frames.rotate(q, v), rot.apply(v), atol=1e-13)
+    assert np.allclose(frames.rotate_inverse(q, v), rot.inv().apply(v), atol=1e-13)
+
+
+def test_nn_io_layout_roundtrip():
+    """form_nn_output (record_planner.py:61-72) and get_wpts_world (nn_planner.py:123-134) are inverse maps; the motion
+    vector has the reference's 24-float layout (record_planner.py:43-48)."""
+    from neo_planner_b200 import frames
+    rng = np.random.default_rng(4)
+    B = 6
+    q = rng.normal(size=(B, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    gp = rng.normal(size=(B, 3)); gv = rng.normal(size=(B, 3)); lv = rng.normal(size=(B, 3))
+    iw = rng.normal(size=(B, 2, 2)) + 3
+    local = frames.form_nn_output(q, gp, 2.0, iw)
+    back, ts = frames.wpts_world(q, gp, np.concatenate([local, np.ones((B, 3))], axis=1))
+    assert np.allclose(back, iw, atol=1e-12) and ts.shape == (B, 3)
+    depth = rng.uniform(0.2, 9.0, size=(B, 48, 64))
+    target = rng.normal(size=(B, 2, 2))
+    dn, motion = frames.form_nn_input(depth, lv, q, gp, gv, 2.0, gp + 0.1, gv, target)
+    assert dn.dtype == np.uint8 and dn.max() == 255 and motion.shape == (B, 24)
+    assert np.allclose(motion[:, :3], lv) and np.allclose(motion[:, 3:12], frames.rotation_matrix(q).reshape(B, 9))
+    tp = np.concatenate([target[:, 0], np.full((B, 1), 2.0)], axis=1)
+    assert np.allclose(frames.rotate(q, motion[:, 18:21]) + gp, tp, atol=1e-12)
+
+
+def test_record_schema_readable_by_reference_trainer(tmp_path):
+    """Rows follow record_planner.py:95-129; the reference's DataReader slices row[1:-9] / row[-9:] (nn_trainer.py:71-94)."""
+    import pandas as pd
+    from neo_planner_b200 import record
+    assert record.TABLE_HEADER[:4] == ['id', 'drone_vel_x', 'drone_vel_y', 'drone_vel_z']
+    assert record.TABLE_HEADER[4:13] == ['R11', 'R12', 'R13', 'R21', 'R22', 'R23', 'R31', 'R32', 'R33']
+    assert record.TABLE_HEADER[13:25] == ['init_pos_x', 'init_pos_y', 'init_pos_z', 'init_vel_x', 'init_vel_y', 'init_vel_z',
+                                          'target_pos_x', 'target_pos_y', 'target_pos_z', 'target_vel_x', 'target_vel_y',
+                                          'target_vel_z']
+    assert record.TABLE_HEADER[25:] == ['wpts1_x', 'wpts1_y', 'wpts1_z', 'wpts2_x', 'wpts2_y', 'wpts2_z', 'ts1', 'ts2', 'ts3']
+    rng = np.random.default_rng(0)
+    motion = rng.normal(size=(5, 24)); wl = rng.normal(size=(5, 6)); ts = rng.uniform(1, 4, size=(5, 3))
+    ids = record.make_ids(5)
+    csv = tmp_path / 'training_data' / 'train.csv'
+    record.append_csv(str(csv), record.training_rows(ids[:3], motion[:3], wl[:3], ts[:3]))
+    record.append_csv(str(csv), record.training_rows(ids[3:], motion[3:], wl[3:], ts[3:]))
+    back = pd.read_csv(csv)
+    assert list(back.columns) == record.TABLE_HEADER and len(back) == 5 and len(set(back['id'])) == 5
+    for i, row in back.iterrows():
+        assert row['id'][0] == 't' and int(row['id'][1:]) > 0
+        assert np.allclose(row.iloc[1:-9].values.astype(float), motion[i]) and np.allclose(row.iloc[-9:].values.astype(float),
+                                                                                          np.concatenate([wl[i], ts[i]]))
+
+
+def test_initializer_network_shapes():
+    import torch
+    from neo_planner_b200 import initializer
+    torch.manual_seed(0)
+    for cls in (initializer.PlannerNet, initializer.PlannerNetConv):
+        net = cls().eval()
+        x = torch.rand(2, initializer.IMG_WIDTH * initializer.IMG_HEIGHT + 24)
+        with torch.no_grad():
+            y = net(x)
+        assert y.shape == (2, 9) and torch.isfinite(y).all()
+    n_params = sum(p.numel() for p in initializer.PlannerNet().parameters())
+    assert 11_000_000 < n_params < 12_000_000          # ResNet-18 trunk (1-channel stem) + the small heads
