@@ -122,6 +122,16 @@ def c_port_run(wl, count=256):
     return dict(value=count / dt, cores=1, kind='port-c', sample=f'first {count} problems, 1 thread', ok=int(out['ok'].sum()))
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_optimize launch from the committed `ncu --set full` capture
+    (profiles/ncu_k_optimize.json), or None when no capture exists for this workload."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_k_optimize.json')))
+        return d[name]['dram_bytes_read'] + d[name]['dram_bytes_write']
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -287,13 +297,13 @@ def main():
         b.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    launches = h.launch_count() - launches0        # kernels of this library launched inside the timed region
     # keep the GPU under the same load a little longer if the timed region was too short to sample clocks
     t_extra = time.perf_counter()
     while len(sampler.samples) < 20 and time.perf_counter() - t_extra < 2.0:
         step_device()
         torch.cuda.synchronize()
     clocks = sampler.result()
-    launches = h.launch_count() - launches0 if len(evs) else 0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if distributed:
@@ -327,8 +337,8 @@ def main():
     if distributed:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world_size * B * Ke / float(t_e2e.item())
-    h2d = 8 * (B * n + 12 * B + B * 4 * nq + M)
-    d2h = 8 * B * (n + M + 12 * M + 4) + 4 * B * 6 + 8 * B * 3
+    h2d = world_size * 8 * (B * n + 12 * B + B * 4 * nq + M)                 # whole job, all ranks
+    d2h = world_size * (8 * B * (n + M + 12 * M + 4) + 4 * B * 6 + 8 * B * 3)
     assert np.array_equal(out_host['ok'], out_i[B:2 * B].cpu().numpy())      # both paths computed the same thing
 
     line = None
@@ -346,9 +356,9 @@ def main():
                 'evals_per_s': world_size * evals / (step_ms * 1e-3), 'mean_evals_per_traj': evals / B, 'ok_fraction': ok_frac,
                 'clocks': clocks,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke},
-                'gpu_launches': int(launches),
+                'gpu_launches': int(launches) * world_size,
                 'roofline': {'bound': 'fp64', 'kernel': 'k_optimize', 'achieved': ach_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                             'frac': ach_tflops / fp64_peak, 'traffic': None,
+                             'frac': ach_tflops / fp64_peak, 'traffic': ncu_traffic(wl['name']),
                              'peak_source': 'measured in this run (neo_fp64_peak DFMA microbenchmark; MEASURED_PEAKS.json has no fp64 figure)',
                              'flops_per_launch': flops, 'l2_gather_bytes_per_launch': l2_bytes,
                              'hbm': {'bound': 'hbm', 'achieved': hbm_bytes / (step_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
