@@ -33,28 +33,41 @@ METRIC = 'optimized trajectories/sec to convergence'
 UNIT = 'traj/s'
 
 
-def workload(name, rank):
-    """Seeded problem set of one rank. Returns dict(world, cfg, M, head, tail, q0, ts0, retry_q, retry_ts)."""
+def workload(name, rank, world_size=1):
+    """Seeded problem set of one rank. Returns dict(worlds, cfg, M, head, tail, map_ids, q0, ts0, retry_q, retry_ts).
+    c2: 1,024 problems on one world per rank (weak scaling). c5: 16,384 problems, M = 10, 1200x1200 @0.05 m map per rank.
+    c4: 65,536 problems = 256 worlds x 256 pairs in total, worlds sharded over the ranks (strong scaling)."""
+    from neo_planner_b200 import sharding
     cfg = YamlConfig()
     if name == 'c5':
-        M, B, dense = 10, 16384, True
+        M, per_world, dense, world_ids = 10, 16384, True, [rank]
+    elif name == 'c4':
+        M, per_world, dense, world_ids = 3, 256, False, sharding.shard_worlds(256, world_size, rank)
     else:
-        M, B, dense = 3, 1024, False
+        M, per_world, dense, world_ids = 3, 1024, False, [rank]
     cfg.init_wpts_num = M - 1
-    world = make_world(rank, dense=dense)
-    head, tail = make_problems(world, B, M=M)
+    worlds, heads, tails, ids = [], [], [], []
+    for slot, wid in enumerate(world_ids):
+        w = make_world(wid, dense=dense)
+        a, b = make_problems(w, per_world, M=M)
+        worlds.append(w); heads.append(a); tails.append(b); ids.append(np.full(per_world, slot, np.int32))
+    head, tail, map_ids = np.concatenate(heads), np.concatenate(tails), np.concatenate(ids)
     q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
     rq, rts = guesses.retry_guesses(cfg, head, tail, M, 4, rng=np.random.default_rng(77_000 + rank))
-    return dict(name=name, world=world, cfg=cfg, M=M, B=B, head=head, tail=tail, q0=q0, ts0=ts0, retry_q=rq, retry_ts=rts)
+    return dict(name=name, world=worlds[0], worlds=worlds, cfg=cfg, M=M, B=len(head), head=head, tail=tail,
+                map_ids=map_ids if len(worlds) > 1 else None, q0=q0, ts0=ts0, retry_q=rq, retry_ts=rts,
+                scaling='strong' if name == 'c4' else 'weak')
 
 
 def describe(wl, n_gpus):
     w = wl['world']
-    return {'workload': f"{wl['B']} start-goal pairs per GPU on one shared {w.H}x{w.W} @{w.res} m random-pillar map per GPU, "
-                        f"M={wl['M']} pieces, expert straight-line init, warm_start_plan semantics (<=5 attempts), "
-                        f"planner_config.yaml parameters (BASELINE.json configs[{1 if wl['name'] == 'c2' else 4}])",
-            'problems_per_gpu': wl['B'], 'pieces': wl['M'], 'map': f'{w.H}x{w.W}@{w.res}', 'max_attempts': 5,
-            'sharding': f'{n_gpus} rank(s), one world per rank, NCCL all-gather of result records' if n_gpus > 1 else 'single GPU',
+    cfgidx = {'c2': 1, 'c4': 3, 'c5': 4}[wl['name']]
+    maps = f"{len(wl['worlds'])} {w.H}x{w.W} @{w.res} m random-pillar map(s) per GPU"
+    return {'workload': f"{wl['B']} start-goal pairs per GPU on {maps}, M={wl['M']} pieces, expert straight-line init, "
+                        f"warm_start_plan semantics (<=5 attempts), planner_config.yaml parameters (BASELINE.json configs[{cfgidx}])",
+            'problems_per_gpu': wl['B'], 'pieces': wl['M'], 'map': f'{w.H}x{w.W}@{w.res}', 'maps_per_gpu': len(wl['worlds']),
+            'max_attempts': 5,
+            'sharding': f'{n_gpus} rank(s), worlds sharded over ranks, NCCL all-gather of result records' if n_gpus > 1 else 'single GPU',
             'l2': 'flushed between timed steps (256 MiB write)'}
 
 
@@ -62,11 +75,16 @@ def describe(wl, n_gpus):
 _W = {}
 
 
+def cpu_sample_workload(name):
+    """The CPU arms time a bounded sample: the problems of the first world of the workload."""
+    return workload(name, 0, 256 if name == 'c4' else 1)
+
+
 def _pool_init(name, rank):
     import warnings
     warnings.filterwarnings('ignore')
     from oracle import minco_ref
-    wl = workload(name, rank)
+    wl = cpu_sample_workload(name)
     w = wl['world']
     _W['wl'] = wl
     _W['grid'] = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
@@ -93,7 +111,7 @@ def cpu_reference_run(name, steps, warmup, per_step=None):
     per_step = per_step or max(16, 2 * cores)
     ctx = mp.get_context('fork')
     with ctx.Pool(cores, initializer=_pool_init, initargs=(name, 0)) as pool:
-        B = 1024 if name == 'c2' else 16384
+        B = {'c2': 1024, 'c4': 256, 'c5': 16384}[name]
         k0 = 0
         for _ in range(warmup):
             pool.map(_pool_plan, [(k0 + i) % B for i in range(per_step)], chunksize=1)
@@ -183,7 +201,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c5'])
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c4', 'c5'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -194,7 +212,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        wl = workload(args.workload, 0)
+        wl = cpu_sample_workload(args.workload)
         r = cpu_reference_run(args.workload, K, args.warmup)
         sample = (f"{r['per_step']} plans per step x {K} steps (problems of the same seeded workload, cycled), "
                   f"multiprocessing.Pool({r['cores']}), Python+scipy restatement of the reference (oracle/minco_ref.py)")
@@ -211,7 +229,7 @@ def main():
     # CPU baseline first (rank 0, N = 1 only): fork the worker pool before CUDA is initialised in this process
     cpu_base = None
     if world_size == 1 and not args.no_cpu_baseline:
-        wl0 = workload(args.workload, 0)
+        wl0 = cpu_sample_workload(args.workload)
         r = cpu_reference_run(args.workload, steps=4, warmup=1)
         cpu_base = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                     'sample': f"{r['problems']} plans of the same workload (first problems, cycled), Python+scipy "
@@ -232,11 +250,13 @@ def main():
     if distributed:
         dist.init_process_group('nccl', device_id=dev)
 
-    wl = workload(args.workload, rank)
+    wl = workload(args.workload, rank, world_size)
     cfg, M, B, world = wl['cfg'], wl['M'], wl['B'], wl['world']
     n, nq = 3 * M - 2, 2 * (M - 1)
-    h = lib.Handle(cfg, local_rank, 1)
-    h.set_map_occupancy(0, world.H, world.W, world.res, world.ox, world.oy, world.occ)     # device EDT build
+    h = lib.Handle(cfg, local_rank, len(wl['worlds']))
+    for slot, w_ in enumerate(wl['worlds']):
+        h.set_map_occupancy(slot, w_.H, w_.W, w_.res, w_.ox, w_.oy, w_.occ)                # device EDT build
+    ids_d = None if wl['map_ids'] is None else torch.from_numpy(wl['map_ids']).to(dev)
     fp64_peak = h.fp64_peak()
 
     # ---- inputs resident in HBM ------------------------------------------------------------------------------
@@ -269,7 +289,8 @@ def main():
     def step_device():
         st = torch.cuda.current_stream().cuda_stream
         assert st != 0
-        h._ck(h.lib.neo_optimize_dev(h.h, B, M, x0.data_ptr(), None, head.data_ptr(), tail.data_ptr(), None, rq.data_ptr(),
+        h._ck(h.lib.neo_optimize_dev(h.h, B, M, x0.data_ptr(), None, head.data_ptr(), tail.data_ptr(),
+                                     None if ids_d is None else ids_d.data_ptr(), rq.data_ptr(),
                                      rtau_d.data_ptr(), 0, 5, C.byref(res), C.c_void_p(st)))
         if distributed:
             dist.all_gather_into_tensor(all_f, out_f)
@@ -318,7 +339,7 @@ def main():
     evals = float(nfev.sum().item())
     flops = 1280.0 * M * evals + 50.0 * wk[0].item() + 65.0 * wk[1].item() + 56.0 * wk[2].item()
     l2_bytes = 8.0 * wk[0].item() + 16.0 * wk[2].item()
-    hbm_bytes = B * (8 * n + 96 + 8 * (12 * M + M + 4) + 12) + world.H * world.W * 32
+    hbm_bytes = B * (8 * n + 96 + 8 * (12 * M + M + 4) + 12) + len(wl['worlds']) * world.H * world.W * 32
     kern_ms = total_ms / K if not distributed else None
     # kernel-only duration (single GPU: the step IS one kernel launch + a 4-byte memset)
     step_ms = total_ms / K
@@ -327,12 +348,12 @@ def main():
     out_host = lib.Handle.alloc_result(B, M)
     hp, tp = lib.pad_state(wl['head']), lib.pad_state(wl['tail'])
     for _ in range(2):
-        h.optimize(M, wl['q0'], wl['ts0'], hp, tp, None, wl['retry_q'], wl['retry_ts'], 5, out=out_host)
+        h.optimize(M, wl['q0'], wl['ts0'], hp, tp, wl['map_ids'], wl['retry_q'], wl['retry_ts'], 5, out=out_host)
     barrier()
     Ke = max(3, min(K, 50))
     t0 = time.perf_counter()
     for _ in range(Ke):
-        h.optimize(M, wl['q0'], wl['ts0'], hp, tp, None, wl['retry_q'], wl['retry_ts'], 5, out=out_host)
+        h.optimize(M, wl['q0'], wl['ts0'], hp, tp, wl['map_ids'], wl['retry_q'], wl['retry_ts'], 5, out=out_host)
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -351,7 +372,7 @@ def main():
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         ach_tflops = flops / (step_ms * 1e-3) / 1e12
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world_size, 'steps': K, 'warmup': W,
-                'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': wl['scaling'], 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': describe(wl, world_size),
                 'evals_per_s': world_size * evals / (step_ms * 1e-3), 'mean_evals_per_traj': evals / B, 'ok_fraction': ok_frac,
                 'clocks': clocks,
