@@ -272,7 +272,7 @@ def main():
     rec_d = n + M + 12 * M + 4
     out_f = torch.zeros(B * rec_d, dtype=torch.float64, device=dev)
     out_i = torch.zeros(B * 6, dtype=torch.int32, device=dev)
-    work = torch.zeros(B * 3, dtype=torch.int64, device=dev)
+    work = torch.zeros(B * 4, dtype=torch.int64, device=dev)
     off = np.cumsum([0, B * n, B * M, B * 12 * M]) * 8
     res = lib.Result()
     res.x, res.ts, res.coeffs, res.costs = (out_f.data_ptr() + int(o) for o in off)
@@ -335,7 +335,7 @@ def main():
     # ---- results of the last step: work accounting + sanity ----------------------------------------------------
     ok_frac = float(out_i[B:2 * B].float().mean().item())
     nfev = out_i[5 * B:6 * B].double()
-    wk = work.view(B, 3).double().sum(0)
+    wk = work.view(B, 4).double().sum(0)
     evals = float(nfev.sum().item())
     flops = 1280.0 * M * evals + 50.0 * wk[0].item() + 65.0 * wk[1].item() + 56.0 * wk[2].item()
     l2_bytes = 8.0 * wk[0].item() + 16.0 * wk[2].item()
@@ -359,7 +359,7 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world_size * B * Ke / float(t_e2e.item())
     h2d = world_size * 8 * (B * n + 12 * B + B * 4 * nq + M)                 # whole job, all ranks
-    d2h = world_size * (8 * B * (n + M + 12 * M + 4) + 4 * B * 6 + 8 * B * 3)
+    d2h = world_size * (8 * B * (n + M + 12 * M + 4) + 4 * B * 6 + 8 * B * 4)
     assert np.array_equal(out_host['ok'], out_i[B:2 * B].cpu().numpy())      # both paths computed the same thing
 
     line = None

@@ -115,8 +115,9 @@ typedef struct {
     int32_t *nit;      /* (B)     sum of res.nit over attempts whose minimize() returned (EP:230)      */
     int32_t *runs;     /* (B)     number of such attempts (opt_running_times, EP:232)                  */
     int32_t *nfev;     /* (B)     fused cost+grad evaluations over all attempts                        */
-    int64_t *work;     /* (B,3) or NULL: samples, velocity-violating samples, colliding samples summed
-                                  over all evaluations (for the roofline flop count)                   */
+    int64_t *work;     /* (B,4) or NULL: samples, velocity-violating samples, colliding samples summed over all
+                                  evaluations of attempts 0..attempt (for the roofline flop count), and the
+                                  nanoseconds those attempts occupied a warp (critical-path accounting)      */
 } neo_result;
 
 /* warm_start_plan (EP:186-203) for B problems: attempt 0 starts from (q0, ts0) through plan_once

@@ -147,6 +147,7 @@ struct OptOut {
 // cancel_word/cancel_mask: when (*cancel_word & cancel_mask) becomes non-zero (an earlier attempt of the same problem
 // has been accepted, so this speculative attempt can never be the returned one) the run stops with ST_CANCELLED.
 constexpr int ST_CANCELLED = 7;
+template <int MODE>
 __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
                                    double x0l, OptOut &o, const unsigned *cancel_word = nullptr,
                                    unsigned cancel_mask = 0u)
@@ -167,7 +168,7 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
         const bool same = !first && __all_sync(FULL, !mine || x == xlast);
         if (!same) {
             EvalOut ev;
-            eval_fg(P, map, m, M, lane, x, true, ev);
+            eval_fg<MODE>(P, map, m, M, lane, x, true, ev);
             o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
             if (ev.status) { o.status = ev.status; o.nit = nit; o.nfev = nfev; o.x = x; return; }
             f = ev.f; g = mine ? ev.g : 0.0; nfev++; xlast = x;

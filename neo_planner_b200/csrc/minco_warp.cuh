@@ -30,6 +30,13 @@
 namespace neo {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// Phase timestamps for the development latency probe (k_eval_ticks in neoopt.cu); compiled out everywhere else.
+#ifdef NEO_TICKS
+#define NEO_TICK(i) do { __syncwarp(); if (ticks) ticks[i] = clock64(); } while (0)
+#else
+#define NEO_TICK(i) do { } while (0)
+#endif
 constexpr int HIST = 10;        // L-BFGS memory (maxcor, EP:220)
 
 struct DevParams {
@@ -73,13 +80,18 @@ struct WarpMem {
     double *Y;     // [HIST][n]
     double *rho;   // [HIST]
     double *al;    // [HIST]   two-loop recursion coefficients
+    double *red;   // [15][33] per-lane partial sums of the sample loop (padded rows; SAMPLE_ALL_PIECES)
+    double *lw;    // [M][2]   first lane and lane count of each piece (SAMPLE_ALL_PIECES)
+    double *pc;    // [M][2]   per-piece feasibility / collision cost
+    double *nsprev; // [M]     sample counts the cached lane assignment was computed for (-1: none)
+    double *asg;   // [32]     cached lane assignment: piece + 16 * width + 1024 * rank
 };
 
 __host__ __device__ inline int warp_mem_doubles(int M)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST;
+              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + 15 * 33 + 4 * M + M + 32;
     return (tot + 1) & ~1;
 }
 
@@ -107,7 +119,12 @@ __device__ inline WarpMem carve(double *base, int M)
     m.S = base; base += HIST * n;
     m.Y = base; base += HIST * n;
     m.rho = base; base += HIST;
-    m.al = base;
+    m.al = base; base += HIST;
+    m.red = base; base += 15 * 33;
+    m.lw = base; base += 2 * M;
+    m.pc = base; base += 2 * M;
+    m.nsprev = base; base += M;
+    m.asg = base;
     return m;
 }
 
@@ -163,6 +180,14 @@ __device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane)
         v[0] = keep + __shfl_xor_sync(FULL, send, 2);
     }
     v[0] += __shfl_xor_sync(FULL, v[0], 1);
+}
+
+// Called when a warp starts on a new problem: head/tail states into shared memory, cached lane assignment dropped.
+__device__ __forceinline__ void begin_problem(const WarpMem &m, int M, int lane, const double *head, const double *tail)
+{
+    if (lane < 6) { m.ht[lane] = head[lane]; m.ht[6 + lane] = tail[lane]; }
+    if (lane < M) { m.nsprev[lane] = -1.0; m.pc[2 * lane] = 0.0; m.pc[2 * lane + 1] = 0.0; }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -281,6 +306,77 @@ struct EvalOut {
     unsigned ns, nv, nc;   // samples, velocity-violating samples, colliding samples (work accounting)
 };
 
+constexpr int SAMPLE_BY_PIECE = 0;   // M <= 4
+constexpr int SAMPLE_ALL_PIECES = 1; // M >= 5
+
+// One sample j of one piece (EP:399-466): position/velocity, ESDF lookup, both penalties and their contributions to
+// acc[0..11] = dW/dc (slot 2k+d), acc[12] = dW/dT, acc[13] = feasibility cost, acc[14] = collision cost.
+__device__ __forceinline__ void sample_point(const DevParams &P, const MapView &map, const double (&cx)[6],
+                                             const double (&cy)[6], int j, int ns, double inv_ns, bool want_grad,
+                                             double (&acc)[16], EvalOut &out, int &bad)
+{
+    const double t = (double)j * P.dt;               // np.arange(0, T_max, dt)[j] (EP:251)
+    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
+    const double px = cx[0] + cx[1] * t + cx[2] * t2 + cx[3] * t3 + cx[4] * t4 + cx[5] * t5;
+    const double py = cy[0] + cy[1] * t + cy[2] * t2 + cy[3] * t3 + cy[4] * t4 + cy[5] * t5;
+    const double b1[6] = {0.0, 1.0, 2.0 * t, 3.0 * t2, 4.0 * t3, 5.0 * t4};
+    const double vx = cx[1] + cx[2] * b1[2] + cx[3] * b1[3] + cx[4] * b1[4] + cx[5] * b1[5];
+    const double vy = cy[1] + cy[2] * b1[2] + cy[3] * b1[3] + cy[4] * b1[4] + cy[5] * b1[5];
+    const double omg = (j == 0 || j == ns - 1) ? 0.5 : 1.0;   // EP:407
+    // collision lookup (EP:415-417): nearest cell, index = int((p - origin)/res), trunc toward zero (ESDF:61-65).
+    // The quotient is first formed with the reciprocal; the exact IEEE division is only redone when that estimate is
+    // within 1e-9 of an integer, so the truncated index is always the reference's.
+    const double dy = py - map.oy, dx = px - map.ox;
+    double fr = dy * map.inv_res, fc = dx * map.inv_res;
+    double tr = trunc(fr), tc = trunc(fc);
+    {   // |estimate - exact quotient| <= 4.5e-16 |q| < 1e-9 for every in-map index (|q| < 2^20)
+        const double er = fabs(fr - tr), ec = fabs(fc - tc);
+        if (er < 1e-9 || er > 1.0 - 1e-9) { fr = dy / map.res; tr = trunc(fr); }
+        if (ec < 1e-9 || ec > 1.0 - 1e-9) { fc = dx / map.res; tc = trunc(fc); }
+    }
+    if (fr != fr || fc != fc) bad = 6;                 // int(nan) raises ValueError
+    const bool inside = tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W;
+    double dis = 10000.0;
+    const Cell *cell = map.cells;
+    if (inside) {
+        cell = map.cells + ((size_t)(int)tr * map.W + (int)tc);
+        dis = __ldg(&cell->d);
+    }
+    const double vv = (vx * vx + vy * vy) - P.v_max2;
+    const double vd = P.safe_dis - dis;
+    out.ns++;
+    if (vv > 0.0) {       // feasibility (EP:409-413, EP:441-451)
+        const double vv2 = vv * vv, vv3 = vv2 * vv;
+        acc[13] += (omg * P.dt) * vv3;
+        if (want_grad) {
+            const double K = (3.0 * P.dt * omg) * vv2;
+            const double ax = 2.0 * cx[2] + 6.0 * t * cx[3] + 12.0 * t2 * cx[4] + 20.0 * t3 * cx[5];
+            const double ay = 2.0 * cy[2] + 6.0 * t * cy[3] + 12.0 * t2 * cy[4] + 20.0 * t3 * cy[5];
+            const double v2t = 2.0 * (ax * vx + ay * vy);
+            const double kx = (P.w2 * K) * (2.0 * vx), ky = (P.w2 * K) * (2.0 * vy);
+#pragma unroll
+            for (int k = 1; k < 6; k++) { acc[2 * k] += b1[k] * kx; acc[2 * k + 1] += b1[k] * ky; }
+            acc[12] += P.w2 * ((omg * vv3 + K * v2t * (double)j) * inv_ns);
+        }
+        out.nv++;
+    }
+    if (vd > 0.0) {       // collision (EP:418-422, EP:453-466); outside the map dis = 10000 never violates
+        const double vd2 = vd * vd, vd3 = vd2 * vd;
+        acc[14] += (omg * P.dt) * vd3;
+        if (want_grad) {
+            const double2 g = __ldg(reinterpret_cast<const double2 *>(cell));
+            const double K = (3.0 * P.dt * omg) * vd2;
+            const double p2t = -(g.x * vx + g.y * vy);
+            const double kx = -(P.w3 * K) * g.x, ky = -(P.w3 * K) * g.y;
+            const double b0[6] = {1.0, t, t2, t3, t4, t5};
+#pragma unroll
+            for (int k = 0; k < 6; k++) { acc[2 * k] += b0[k] * kx; acc[2 * k + 1] += b0[k] * ky; }
+            acc[12] += P.w3 * ((omg * vd3 + K * p2t * (double)j) * inv_ns);
+        }
+        out.nc++;
+    }
+}
+
 // tau -> T for all pieces; returns 0 or the status the reference's exception maps to. Also fills 1/T^k.
 __device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem &m, int M, int lane, double xl,
                                               double &e_out)
@@ -304,6 +400,7 @@ __device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem 
         const int ns = (int)(T / P.dt);                       // sample_num = int(T/delta_t) (EP:401)
         m.nsd[2 * lane] = (double)ns;
         m.nsd[2 * lane + 1] = 1.0 / (double)ns;
+        m.pc[2 * lane] = 0.0; m.pc[2 * lane + 1] = 0.0;        // a piece without samples contributes no penalty
     }
     e_out = e;
     bad = __reduce_max_sync(FULL, bad);
@@ -311,9 +408,11 @@ __device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem 
     return bad;
 }
 
+template <int MODE>
 __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
-                                        double xl, bool want_grad, EvalOut &out)
+                                        double xl, bool want_grad, EvalOut &out, long long *ticks = nullptr)
 {
+    NEO_TICK(0);
     const int nq = 2 * (M - 1);
     out.status = 0; out.ns = out.nv = out.nc = 0;
     out.g = 0.0;
@@ -323,9 +422,12 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     if (bad) { out.status = bad; out.f = 0.0; out.costs[0] = out.costs[1] = out.costs[2] = out.costs[3] = 0.0; return; }
 
     // ---- coefficients (EP:261-336) ----------------------------------------------------------------
+    NEO_TICK(1);
     load_nodes(m, M, lane, xl);
     solve_nodes(m, M, lane);
+    NEO_TICK(2);
     hermite_coeffs(m, M, lane);
+    NEO_TICK(3);
 
     // ---- energy + time (EP:345-390): lane (piece i, dim d) -------------------------------------------
     if (lane < 2 * M) {
@@ -352,91 +454,104 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         costs1 += m.ts[i];
     }
 
-    // ---- sampled penalties (EP:392-466): lanes over the samples of one piece at a time ---------------
+    NEO_TICK(4);
+    // ---- sampled penalties (EP:392-466) -----------------------------------------------------------------
     double costs2 = 0.0, costs3 = 0.0;
-    for (int i = 0; i < M; i++) {
-        const int ns = (int)m.nsd[2 * i];                    // int(T/delta_t) (EP:401)
-        const double inv_ns = m.nsd[2 * i + 1];
-        const double *ci = m.c + 12 * i;
-        double cx[6], cy[6];
+    if (MODE == SAMPLE_BY_PIECE) {
+        // few pieces (M <= 4): one piece at a time, lanes over its samples, 16-value butterfly reduction per piece
+        for (int i = 0; i < M; i++) {
+            const int ns = (int)m.nsd[2 * i];                    // int(T/delta_t) (EP:401)
+            const double inv_ns = m.nsd[2 * i + 1];
+            const double *ci = m.c + 12 * i;
+            double cx[6], cy[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) { cx[k] = ci[2 * k]; cy[k] = ci[2 * k + 1]; }
-        double acc[16];
+            for (int k = 0; k < 6; k++) { cx[k] = ci[2 * k]; cy[k] = ci[2 * k + 1]; }
+            double acc[16];
 #pragma unroll
-        for (int s = 0; s < 16; s++) acc[s] = 0.0;
-        for (int j = lane; j < ns; j += 32) {
-            const double t = (double)j * P.dt;               // np.arange(0, T_max, dt)[j] (EP:251)
-            const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
-            const double px = cx[0] + cx[1] * t + cx[2] * t2 + cx[3] * t3 + cx[4] * t4 + cx[5] * t5;
-            const double py = cy[0] + cy[1] * t + cy[2] * t2 + cy[3] * t3 + cy[4] * t4 + cy[5] * t5;
-            const double b1[6] = {0.0, 1.0, 2.0 * t, 3.0 * t2, 4.0 * t3, 5.0 * t4};
-            const double vx = cx[1] + cx[2] * b1[2] + cx[3] * b1[3] + cx[4] * b1[4] + cx[5] * b1[5];
-            const double vy = cy[1] + cy[2] * b1[2] + cy[3] * b1[3] + cy[4] * b1[4] + cy[5] * b1[5];
-            const double omg = (j == 0 || j == ns - 1) ? 0.5 : 1.0;   // EP:407
-            // collision lookup (EP:415-417): nearest cell, index = int((p - origin)/res), trunc toward zero
-            // (ESDF:61-65). The quotient is first formed with the reciprocal; the exact IEEE division is only
-            // redone when that estimate is within 1e-9 of an integer, so the truncated index is always the
-            // reference's.
-            const double dy = py - map.oy, dx = px - map.ox;
-            double fr = dy * map.inv_res, fc = dx * map.inv_res;
-            double tr = trunc(fr), tc = trunc(fc);
-            {   // |estimate - exact quotient| <= 4.5e-16 |q| < 1e-9 for every in-map index (|q| < 2^20)
-                const double er = fabs(fr - tr), ec = fabs(fc - tc);
-                if (er < 1e-9 || er > 1.0 - 1e-9) { fr = dy / map.res; tr = trunc(fr); }
-                if (ec < 1e-9 || ec > 1.0 - 1e-9) { fc = dx / map.res; tc = trunc(fc); }
+            for (int s2 = 0; s2 < 16; s2++) acc[s2] = 0.0;
+            for (int j = lane; j < ns; j += 32) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
+            warp_reduce16(acc, lane);
+            const int slot = lane >> 1;
+            const double tot = acc[0];
+            if (!(lane & 1)) {
+                if (slot < 12) m.gC[12 * i + slot] += tot;
+                else if (slot == 12) m.gT[i] += tot;
             }
-            if (fr != fr || fc != fc) bad = 6;                 // int(nan) raises ValueError
-            const bool inside = tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W;
-            double dis = 10000.0;
-            const Cell *cell = map.cells;
-            if (inside) {
-                cell = map.cells + ((size_t)(int)tr * map.W + (int)tc);
-                dis = __ldg(&cell->d);
-            }
-            // feasibility (EP:409-413, EP:441-451)
-            const double vv = (vx * vx + vy * vy) - P.v_max2;
-            const double vd = P.safe_dis - dis;
-            out.ns++;
-            if (vv > 0.0) {
-                const double vv2 = vv * vv, vv3 = vv2 * vv;
-                acc[13] += (omg * P.dt) * vv3;
-                if (want_grad) {
-                    const double K = (3.0 * P.dt * omg) * vv2;
-                    const double ax = 2.0 * cx[2] + 6.0 * t * cx[3] + 12.0 * t2 * cx[4] + 20.0 * t3 * cx[5];
-                    const double ay = 2.0 * cy[2] + 6.0 * t * cy[3] + 12.0 * t2 * cy[4] + 20.0 * t3 * cy[5];
-                    const double v2t = 2.0 * (ax * vx + ay * vy);
-                    const double kx = (P.w2 * K) * (2.0 * vx), ky = (P.w2 * K) * (2.0 * vy);
+            costs2 += __shfl_sync(FULL, tot, 26);
+            costs3 += __shfl_sync(FULL, tot, 28);
+        }
+    } else {
+        // many pieces: the 32 lanes are split among the pieces in proportion to their sample counts (every piece with
+        // samples gets at least one lane), so a lane only ever accumulates for ONE piece and all pieces are sampled
+        // concurrently: ceil(S/32) rounds instead of sum_i ceil(ns_i/32). Per-lane partial sums go to shared memory
+        // and are added per (piece, slot) in a fixed lane order.
+        int my_piece = 0, my_rank = 0, my_width = 1;
+        const double ns_mine = lane < M ? m.nsd[2 * lane] : 0.0;
+        if (__any_sync(FULL, lane < M && ns_mine != m.nsprev[lane])) {
+            // (re)assign lanes -- only when a sample count changed since the previous evaluation of this problem.
+            // lane i < M owns piece i: every non-empty piece gets one lane up front, the remaining lanes are split in
+            // proportion to the cumulative sample counts; boundaries hi_i, piece of a lane = #boundaries <= lane.
+            const int ns_i = (int)ns_mine;
+            int cum = ns_i, nonempty = ns_i > 0 ? 1 : 0;
 #pragma unroll
-                    for (int k = 1; k < 6; k++) { acc[2 * k] += b1[k] * kx; acc[2 * k + 1] += b1[k] * ky; }
-                    acc[12] += P.w2 * ((omg * vv3 + K * v2t * (double)j) * inv_ns);
+            for (int o = 1; o < 16; o <<= 1) {                  // inclusive scans over lanes 0..M-1 (M <= 10 < 16)
+                const int c2 = __shfl_up_sync(FULL, cum, o), n2 = __shfl_up_sync(FULL, nonempty, o);
+                if (lane >= o) { cum += c2; nonempty += n2; }
+            }
+            const int S = __shfl_sync(FULL, cum, M - 1), pieces = __shfl_sync(FULL, nonempty, M - 1);
+            int hi = 0;
+            if (lane < M && S > 0) hi = nonempty + (int)floor((double)((32 - pieces) * cum) / (double)S);
+            int lo = __shfl_up_sync(FULL, hi, 1);
+            if (lane == 0) lo = 0;
+            if (lane < M) { m.lw[2 * lane] = (double)lo; m.lw[2 * lane + 1] = (double)(hi - lo); m.nsprev[lane] = ns_mine; }
+            for (int i = 0; i < M; i++) my_piece += lane >= __shfl_sync(FULL, hi, i) ? 1 : 0;
+            if (my_piece >= M || S == 0) { my_piece = 0; my_rank = 1 << 20; }       // no samples at all: idle lane
+            else {
+                const int plo = __shfl_sync(FULL, lo, my_piece), phi = __shfl_sync(FULL, hi, my_piece);
+                my_rank = lane - plo; my_width = phi - plo;
+            }
+            m.asg[lane] = (double)(my_piece + 16 * my_width + 1024 * my_rank);
+            __syncwarp();
+        } else {
+            const int v = (int)m.asg[lane];
+            my_piece = v & 15; my_width = (v >> 4) & 63; my_rank = v >> 10;
+        }
+        {
+            const int i = my_piece;
+            const int ns = (int)m.nsd[2 * i];
+            const double inv_ns = m.nsd[2 * i + 1];
+            const double *ci = m.c + 12 * i;
+            double cx[6], cy[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { cx[k] = ci[2 * k]; cy[k] = ci[2 * k + 1]; }
+            double acc[16];
+#pragma unroll
+            for (int s2 = 0; s2 < 16; s2++) acc[s2] = 0.0;
+            for (int j = my_rank; j < ns; j += my_width) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
+#pragma unroll
+            for (int s2 = 0; s2 < 15; s2++) m.red[s2 * 33 + lane] = acc[s2];
+        }
+        __syncwarp();
+        {   // owner (piece i, slot s): slot = lane % 16, two pieces per pass, four interleaved chains in fixed order
+            const int s2 = lane & 15;
+            for (int i = lane >> 4; i < M; i += 2) {
+                const int lo = (int)m.lw[2 * i], w = (int)m.lw[2 * i + 1];
+                const double *p = m.red + (s2 < 15 ? s2 : 0) * 33 + lo;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int k = 0; k < w; k += 4) {
+                    a0 += p[k];
+                    a1 += k + 1 < w ? p[k + 1] : 0.0;
+                    a2 += k + 2 < w ? p[k + 2] : 0.0;
+                    a3 += k + 3 < w ? p[k + 3] : 0.0;
                 }
-                out.nv++;
-            }
-            if (vd > 0.0) {       // collision (EP:418-422, EP:453-466); outside the map dis = 10000 never violates
-                const double vd2 = vd * vd, vd3 = vd2 * vd;
-                acc[14] += (omg * P.dt) * vd3;
-                if (want_grad) {
-                    const double2 g = __ldg(reinterpret_cast<const double2 *>(cell));
-                    const double K = (3.0 * P.dt * omg) * vd2;
-                    const double p2t = -(g.x * vx + g.y * vy);
-                    const double kx = -(P.w3 * K) * g.x, ky = -(P.w3 * K) * g.y;
-                    const double b0[6] = {1.0, t, t2, t3, t4, t5};
-#pragma unroll
-                    for (int k = 0; k < 6; k++) { acc[2 * k] += b0[k] * kx; acc[2 * k + 1] += b0[k] * ky; }
-                    acc[12] += P.w3 * ((omg * vd3 + K * p2t * (double)j) * inv_ns);
-                }
-                out.nc++;
+                const double tot = (a0 + a1) + (a2 + a3);
+                if (s2 < 12) m.gC[12 * i + s2] += tot;
+                else if (s2 == 12) m.gT[i] += tot;
+                else if (s2 < 15) m.pc[2 * i + (s2 - 13)] = tot;
             }
         }
-        warp_reduce16(acc, lane);
-        const int slot = lane >> 1;
-        const double tot = acc[0];
-        if (!(lane & 1)) {
-            if (slot < 12) m.gC[12 * i + slot] += tot;
-            else if (slot == 12) m.gT[i] += tot;
-        }
-        costs2 += __shfl_sync(FULL, tot, 26);
-        costs3 += __shfl_sync(FULL, tot, 28);
+        __syncwarp();
+        for (int i = 0; i < M; i++) { costs2 += m.pc[2 * i]; costs3 += m.pc[2 * i + 1]; }
     }
     bad = __reduce_max_sync(FULL, bad);
     out.ns = __reduce_add_sync(FULL, out.ns);
@@ -448,6 +563,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     if (!want_grad) return;
     __syncwarp();
 
+    NEO_TICK(5);
     // ---- adjoint (EP:494-537) ------------------------------------------------------------------------
     // h_i = H(T_i)^T dW/dc_i: gradient w.r.t. the boundary states of piece i, lane (i, d)
     if (lane < 2 * M) {
@@ -465,6 +581,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         h[10] = 0.5 * a * g3 - a2 * g4 + 0.5 * a3 * g5;
     }
     __syncwarp();
+    NEO_TICK(6);
     // eta_j = dW/d(v_j, a_j) at the interior nodes, then K^T lam = eta by block elimination (lanes 0/1 per dim);
     // the Schur complements of K^T are the transposes of those of K, so D'^-1 from the forward solve is reused.
     {
@@ -500,6 +617,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         if (lane < 2) { m.lam[d] = 0.0; m.lam[2 + d] = 0.0; m.lam[4 * M + d] = 0.0; m.lam[4 * M + 2 + d] = 0.0; }
     }
     __syncwarp();
+    NEO_TICK(7);
     // G rows of interior node j (reference rows 6(j-1)+3 .. 6(j-1)+8), lane (j, d): grad_q and the T-gradient inputs
     if (lane >= 2 && lane < 2 * M) {
         const int j = lane >> 1, d = lane & 1;
@@ -520,6 +638,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         m.gout[d * (M - 1) + (j - 1)] = Gq;              // grad_q[d][j-1] = G[6(j-1)+3][d] (EP:506-508)
     }
     __syncwarp();
+    NEO_TICK(8);
     // grad_T (EP:511-533): piece i < M-1 uses T_i; the last piece re-uses the loop variable T = ts[M-2]
     if (lane < M) {
         const int i = lane;
@@ -554,6 +673,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     __syncwarp();
     out.g = (lane < nq + M) ? m.gout[lane] : 0.0;
     __syncwarp();
+    NEO_TICK(9);
 }
 
 }  // namespace neo

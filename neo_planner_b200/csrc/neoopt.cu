@@ -41,7 +41,7 @@ struct OptArgs {
     double *t_x;                 // (A*B, n)
     double *t_costs;             // (A*B, 4)
     int32_t *t_info;             // (A*B, 4): status, nit, nfev, completed (minimize() returned)
-    long long *t_work;           // (A*B, 3)
+    long long *t_work;           // (A*B, 4): samples, velocity-violating, colliding, nanoseconds on the SM
     unsigned int *p_state;       // (B): bits 0..7 attempts finished, bits 8..15 attempts accepted
     double *x, *ts, *coeffs, *costs;
     int32_t *status, *ok, *attempt, *nit, *runs, *nfev;
@@ -64,6 +64,7 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // as soon as an earlier attempt of its problem is accepted. With many problems per SM the queue reaches the retries
 // only when first attempts are finished, so speculation costs nothing; with few problems it halves the tail.
 // The warp whose completion resolves a problem assembles its outputs (final coefficients included).
+template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
@@ -82,9 +83,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
         unsigned bits = 1u << at;
         const unsigned seen = *reinterpret_cast<volatile unsigned *>(a.p_state + b);
         if (!(seen & lower_ok)) {
-            if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
+            unsigned long long t_start;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+            begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
             const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-            __syncwarp();
             double x0l = 0.0;
             int st0 = 0;
             if (at == 0) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
             OptOut o;
             o.status = st0; o.nit = 0; o.nfev = 0; o.ns = o.nv = o.nc = 0; o.x = 0.0;
             o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
-            if (!st0) lbfgsb_warp(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok);   // else map_T2tau raised (EP:209)
+            if (!st0) lbfgsb_warp<MODE>(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok);   // else map_T2tau raised (EP:209)
             if (o.status != ST_CANCELLED) {
                 const bool completed = o.status < NEO_ST_OVERFLOW;             // minimize() returned (EP:213-233)
                 const bool accepted = completed && !(o.costs[3] * P.w3 > P.collision_cost_tol);   // EP:235-237
@@ -107,8 +109,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
                 if (lane == 0) {
                     a.t_info[(size_t)tid * 4 + 0] = o.status; a.t_info[(size_t)tid * 4 + 1] = o.nit;
                     a.t_info[(size_t)tid * 4 + 2] = o.nfev; a.t_info[(size_t)tid * 4 + 3] = completed ? 1 : 0;
-                    a.t_work[(size_t)tid * 3 + 0] = (long long)o.ns; a.t_work[(size_t)tid * 3 + 1] = (long long)o.nv;
-                    a.t_work[(size_t)tid * 3 + 2] = (long long)o.nc;
+                    unsigned long long t_end;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+                    a.t_work[(size_t)tid * 4 + 0] = (long long)o.ns; a.t_work[(size_t)tid * 4 + 1] = (long long)o.nv;
+                    a.t_work[(size_t)tid * 4 + 2] = (long long)o.nc; a.t_work[(size_t)tid * 4 + 3] = (long long)(t_end - t_start);
                 }
                 if (accepted) bits |= 1u << (8 + at);
                 __threadfence();
@@ -126,20 +130,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
         const unsigned okm = (now >> 8) & 0xffu;
         const int last = okm ? __ffs(okm) - 1 : A - 1;      // returned attempt (EP:196-203)
         int nit = 0, runs = 0, nfev = 0, src = -1, status = 0;
-        long long ns = 0, nv = 0, nc = 0;
+        long long ns = 0, nv = 0, nc = 0, nanos = 0;
         for (int k = 0; k <= last; k++) {
             const size_t t = (size_t)k * a.B + b;
             const int st = __ldcg(a.t_info + t * 4 + 0);
             status = st;
             nfev += __ldcg(a.t_info + t * 4 + 2);
-            ns += __ldcg(a.t_work + t * 3 + 0); nv += __ldcg(a.t_work + t * 3 + 1); nc += __ldcg(a.t_work + t * 3 + 2);
+            ns += __ldcg(a.t_work + t * 4 + 0); nv += __ldcg(a.t_work + t * 4 + 1); nc += __ldcg(a.t_work + t * 4 + 2);
+            nanos += __ldcg(a.t_work + t * 4 + 3);
             if (__ldcg(a.t_info + t * 4 + 3)) { runs++; nit += __ldcg(a.t_info + t * 4 + 1); src = k; }
         }
         if (src >= 0) {      // final (int_wpts, ts) -> ts, coefficients (EP:226-229, TU:182)
             const size_t t = (size_t)src * a.B + b;
             const double xf = lane < n ? __ldcg(a.t_x + t * n + lane) : 0.0;
-            if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
-            __syncwarp();
+            begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
             double e_unused;
             times_from_tau(P, m, M, lane, xf, e_unused);
             load_nodes(m, M, lane, xf);
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
         if (lane == 0) {
             a.status[b] = status; a.ok[b] = okm ? 1 : 0; a.attempt[b] = last; a.nit[b] = nit; a.runs[b] = runs;
             a.nfev[b] = nfev;
-            if (a.work) { a.work[b * 3] = ns; a.work[b * 3 + 1] = nv; a.work[b * 3 + 2] = nc; }
+            if (a.work) { a.work[b * 4] = ns; a.work[b * 4 + 1] = nv; a.work[b * 4 + 2] = nc; a.work[b * 4 + 3] = nanos; }
         }
         __syncwarp();
     }
@@ -173,6 +177,7 @@ struct EvalArgs {
     int32_t *status;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, const EvalArgs a)
 {
     extern __shared__ double smem[];
@@ -180,12 +185,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, 
     const int M = a.M, n = 3 * M - 2, N = 6 * M;
     const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
     for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)a.B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
-        if (lane < 6) { m.ht[lane] = a.head[b * 6 + lane]; m.ht[6 + lane] = a.tail[b * 6 + lane]; }
+        begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
         const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-        __syncwarp();
         const double xl = lane < n ? a.x[b * n + lane] : 0.0;
         EvalOut ev;
-        eval_fg(P, map, m, M, lane, xl, true, ev);
+        eval_fg<MODE>(P, map, m, M, lane, xl, true, ev);
         if (lane < n) a.grad[b * n + lane] = ev.status ? 0.0 : ev.g;
         if (lane < 4) a.costs[b * 4 + lane] = ev.costs[lane];
         if (lane == 0) a.status[b] = ev.status;
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_coeffs(int B, int M, con
     const int nq = 2 * (M - 1), N = 6 * M;
     const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
     for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
-        if (lane < 6) { m.ht[lane] = head[b * 6 + lane]; m.ht[6 + lane] = tail[b * 6 + lane]; }
+        begin_problem(m, M, lane, head + b * 6, tail + b * 6);
         if (lane < M) {
             const double T = ts[b * M + lane];
             m.ts[lane] = T;
@@ -642,7 +646,8 @@ static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm)
 static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 {
     int occ;
-    int rc = prep_kernel(h, k_optimize, a.M, &occ);
+    const bool by_piece = a.M <= 4;       // sampling schedule (minco_warp.cuh): piece by piece for short trajectories
+    int rc = by_piece ? prep_kernel(h, k_optimize<SAMPLE_BY_PIECE>, a.M, &occ) : prep_kernel(h, k_optimize<SAMPLE_ALL_PIECES>, a.M, &occ);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
     const size_t need = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -650,7 +655,7 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     // per-task scratch records + per-problem state word (library-owned, grow-only)
     char *base;
     const size_t o_x = 0, o_c = o_x + sizeof(double) * tasks * n, o_w = o_c + sizeof(double) * tasks * 4,
-                 o_i = o_w + sizeof(long long) * tasks * 3, o_p = o_i + sizeof(int32_t) * tasks * 4,
+                 o_i = o_w + sizeof(long long) * tasks * 4, o_p = o_i + sizeof(int32_t) * tasks * 4,
                  total = o_p + sizeof(unsigned) * a.B;
     if ((rc = dev_buf(h, 6, total, (void **)&base))) return rc;
     a.t_x = (double *)(base + o_x); a.t_costs = (double *)(base + o_c); a.t_work = (long long *)(base + o_w);
@@ -659,7 +664,8 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.counter = h->d_counter;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
-    k_optimize<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    if (by_piece) k_optimize<SAMPLE_BY_PIECE><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    else k_optimize<SAMPLE_ALL_PIECES><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
@@ -668,12 +674,14 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
 {
     int occ;
-    int rc = prep_kernel(h, k_eval, a.M, &occ);
+    const bool by_piece = a.M <= 4;
+    int rc = by_piece ? prep_kernel(h, k_eval<SAMPLE_BY_PIECE>, a.M, &occ) : prep_kernel(h, k_eval<SAMPLE_ALL_PIECES>, a.M, &occ);
     if (rc) return rc;
     const int need = (a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
     a.maps = h->d_maps;
-    k_eval<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    if (by_piece) k_eval<SAMPLE_BY_PIECE><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    else k_eval<SAMPLE_ALL_PIECES><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
@@ -871,7 +879,7 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
         d.costs = c.take<double>(b * 4);
         d.status = c.take<int32_t>(b); d.ok = c.take<int32_t>(b); d.attempt = c.take<int32_t>(b);
         d.nit = c.take<int32_t>(b); d.runs = c.take<int32_t>(b); d.nfev = c.take<int32_t>(b);
-        d.work = c.take<int64_t>(b * 3);
+        d.work = c.take<int64_t>(b * 4);
         if (!pass) {
             void *p;
             if ((rc = dev_buf(h, 3, c.off + 256, &p))) return rc;
@@ -903,7 +911,7 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
         CK(cudaMemcpyAsync(out->nit, d.nit, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out->runs, d.runs, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out->nfev, d.nfev, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        if (out->work) CK(cudaMemcpyAsync(out->work, d.work, sizeof(int64_t) * b * 3, cudaMemcpyDeviceToHost, st));
+        if (out->work) CK(cudaMemcpyAsync(out->work, d.work, sizeof(int64_t) * b * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     }

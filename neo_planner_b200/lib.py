@@ -200,7 +200,7 @@ class Handle:
         return dict(x=np.zeros((B, n)), ts=np.zeros((B, M)), coeffs=np.zeros((B, 6 * M, 2)), costs=np.zeros((B, 4)),
                     status=np.zeros(B, np.int32), ok=np.zeros(B, np.int32), attempt=np.zeros(B, np.int32),
                     nit=np.zeros(B, np.int32), runs=np.zeros(B, np.int32), nfev=np.zeros(B, np.int32),
-                    work=np.zeros((B, 3), np.int64) if work else None)
+                    work=np.zeros((B, 4), np.int64) if work else None)
 
     @staticmethod
     def result_struct(out):
