@@ -304,6 +304,7 @@ struct neo_handle {
     MapView *d_maps = nullptr;
     unsigned int *d_counter = nullptr;
     std::vector<DevBuf> bufs;        // reusable device staging buffers for the host-pointer entry points
+    DevBuf pinned;                   // reusable pinned host staging buffer (neo_optimize)
     std::string err;
     std::mutex mu;
     float last_ms = 0.f;
@@ -349,6 +350,21 @@ static int dev_buf(neo_handle *h, size_t i, size_t bytes, void **out)
         b.p = nullptr; b.cap = 0;
         size_t cap = bytes + bytes / 4 + 256;
         CK(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return NEO_OK;
+}
+
+// grow-only pinned host staging buffer
+static int pin_buf(neo_handle *h, size_t bytes, void **out)
+{
+    DevBuf &b = h->pinned;
+    if (b.cap < bytes) {
+        if (b.p) CK(cudaFreeHost(b.p));
+        b.p = nullptr; b.cap = 0;
+        const size_t cap = bytes + bytes / 4 + 256;
+        CK(cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
         b.cap = cap;
     }
     *out = b.p;
@@ -402,6 +418,7 @@ extern "C" int neo_destroy(neo_handle *h)
     cudaStreamSynchronize(h->stream);
     for (auto &s : h->slots) { if (s.cells) cudaFree(s.cells); if (s.occ) cudaFree(s.occ); }
     for (auto &b : h->bufs) if (b.p) cudaFree(b.p);
+    if (h->pinned.p) cudaFreeHost(h->pinned.p);
     cudaFree(h->d_maps); cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -849,9 +866,26 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
     CK(cudaSetDevice(h->device));
     const size_t n = 3 * M - 2, nq = 2 * (M - 1), N2 = 12 * M, b = B, A1 = max_attempts - 1;
 
-    // host: x0 = [q0, map_T2tau(ts0)] (EP:207-211)
-    std::vector<double> hx0(b * n);
-    std::vector<int32_t> hst(b);
+    // One pinned staging buffer mirrors the device layout: [inputs | outputs]. Inputs are assembled in place
+    // (x0 = [q0, map_T2tau(ts0)], EP:207-211), moved with ONE H2D copy; results come back with ONE D2H copy.
+    struct Lay {
+        size_t x0, head, tail, st0, ids, rq, rtau, in_end, x, ts, coeffs, costs, status, ok, attempt, nit, runs, nfev, work, end;
+    } L;
+    {
+        Carver c{nullptr};
+        auto off = [&](size_t bytes) { c.off = (c.off + 255) & ~(size_t)255; size_t o = c.off; c.off += bytes; return o; };
+        L.x0 = off(8 * b * n); L.head = off(8 * b * 6); L.tail = off(8 * b * 6); L.st0 = off(4 * b); L.ids = off(4 * b);
+        L.rq = off(8 * (b * A1 * nq + 1)); L.rtau = off(8 * NEO_MAX_PIECES); L.in_end = off(0);
+        L.x = off(8 * b * n); L.ts = off(8 * b * M); L.coeffs = off(8 * b * N2); L.costs = off(8 * b * 4);
+        L.status = off(4 * b); L.ok = off(4 * b); L.attempt = off(4 * b); L.nit = off(4 * b); L.runs = off(4 * b);
+        L.nfev = off(4 * b); L.work = off(8 * b * 4); L.end = off(0);
+    }
+    char *dbase, *hbase;
+    if ((rc = dev_buf(h, 3, L.end, (void **)&dbase))) return rc;
+    if ((rc = pin_buf(h, L.end, (void **)&hbase))) return rc;
+
+    double *hx0 = (double *)(hbase + L.x0);
+    int32_t *hst = (int32_t *)(hbase + L.st0);
     bool any_bad = false;
     for (size_t i = 0; i < b; i++) {
         memcpy(&hx0[i * n], q0 + i * nq, sizeof(double) * nq);
@@ -865,56 +899,43 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
         hst[i] = st;
         any_bad = any_bad || st;
     }
-    double rtau[NEO_MAX_PIECES] = {0};
+    double *rtau = (double *)(hbase + L.rtau);
     int rstatus = 0;
-    if (A1) for (int k = 0; k < M; k++) { const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
+    if (A1) for (int k = 0; k < M; k++) { rtau[k] = 0.0; const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
+    memcpy(hbase + L.head, head, 8 * b * 6);
+    memcpy(hbase + L.tail, tail, 8 * b * 6);
+    if (map_ids) memcpy(hbase + L.ids, map_ids, 4 * b);
+    if (A1) memcpy(hbase + L.rq, retry_q, 8 * b * A1 * nq);
 
-    for (int pass = 0; pass < 2; pass++) {
-        Carver c{pass ? (char *)h->bufs[3].p : nullptr};
-        double *d_x0 = c.take<double>(b * n), *d_head = c.take<double>(b * 6), *d_tail = c.take<double>(b * 6);
-        int32_t *d_st0 = c.take<int32_t>(b), *d_ids = c.take<int32_t>(b);
-        double *d_rq = c.take<double>(b * A1 * nq + 1), *d_rtau = c.take<double>(NEO_MAX_PIECES);
-        neo_result d;
-        d.x = c.take<double>(b * n); d.ts = c.take<double>(b * M); d.coeffs = c.take<double>(b * N2);
-        d.costs = c.take<double>(b * 4);
-        d.status = c.take<int32_t>(b); d.ok = c.take<int32_t>(b); d.attempt = c.take<int32_t>(b);
-        d.nit = c.take<int32_t>(b); d.runs = c.take<int32_t>(b); d.nfev = c.take<int32_t>(b);
-        d.work = c.take<int64_t>(b * 4);
-        if (!pass) {
-            void *p;
-            if ((rc = dev_buf(h, 3, c.off + 256, &p))) return rc;
-            continue;
-        }
-        cudaStream_t st = h->stream;
-        CK(cudaMemcpyAsync(d_x0, hx0.data(), sizeof(double) * b * n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_head, head, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_tail, tail, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
-        if (any_bad) CK(cudaMemcpyAsync(d_st0, hst.data(), sizeof(int32_t) * b, cudaMemcpyHostToDevice, st));
-        if (map_ids) CK(cudaMemcpyAsync(d_ids, map_ids, sizeof(int32_t) * b, cudaMemcpyHostToDevice, st));
-        if (A1) {
-            CK(cudaMemcpyAsync(d_rq, retry_q, sizeof(double) * b * A1 * nq, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(d_rtau, rtau, sizeof(double) * M, cudaMemcpyHostToDevice, st));
-        }
-        if (!out->work) d.work = nullptr;
-        CK(cudaEventRecord(h->ev0, st));
-        rc = optimize_dev_impl(h, B, M, d_x0, any_bad ? d_st0 : nullptr, d_head, d_tail, map_ids ? d_ids : nullptr,
-                               A1 ? d_rq : nullptr, A1 ? d_rtau : nullptr, rstatus, max_attempts, &d, st);
-        if (rc) return rc;
-        CK(cudaEventRecord(h->ev1, st));
-        CK(cudaMemcpyAsync(out->x, d.x, sizeof(double) * b * n, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->ts, d.ts, sizeof(double) * b * M, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->coeffs, d.coeffs, sizeof(double) * b * N2, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->costs, d.costs, sizeof(double) * b * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->status, d.status, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->ok, d.ok, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->attempt, d.attempt, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->nit, d.nit, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->runs, d.runs, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out->nfev, d.nfev, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
-        if (out->work) CK(cudaMemcpyAsync(out->work, d.work, sizeof(int64_t) * b * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    }
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(dbase, hbase, L.in_end, cudaMemcpyHostToDevice, st));
+    neo_result d;
+    d.x = (double *)(dbase + L.x); d.ts = (double *)(dbase + L.ts); d.coeffs = (double *)(dbase + L.coeffs);
+    d.costs = (double *)(dbase + L.costs);
+    d.status = (int32_t *)(dbase + L.status); d.ok = (int32_t *)(dbase + L.ok); d.attempt = (int32_t *)(dbase + L.attempt);
+    d.nit = (int32_t *)(dbase + L.nit); d.runs = (int32_t *)(dbase + L.runs); d.nfev = (int32_t *)(dbase + L.nfev);
+    d.work = out->work ? (int64_t *)(dbase + L.work) : nullptr;
+    CK(cudaEventRecord(h->ev0, st));
+    rc = optimize_dev_impl(h, B, M, (const double *)(dbase + L.x0), any_bad ? (const int32_t *)(dbase + L.st0) : nullptr,
+                           (const double *)(dbase + L.head), (const double *)(dbase + L.tail),
+                           map_ids ? (const int32_t *)(dbase + L.ids) : nullptr, A1 ? (const double *)(dbase + L.rq) : nullptr,
+                           A1 ? (const double *)(dbase + L.rtau) : nullptr, rstatus, max_attempts, &d, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaMemcpyAsync(hbase + L.x, dbase + L.x, L.end - L.x, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    memcpy(out->x, hbase + L.x, 8 * b * n);
+    memcpy(out->ts, hbase + L.ts, 8 * b * M);
+    memcpy(out->coeffs, hbase + L.coeffs, 8 * b * N2);
+    memcpy(out->costs, hbase + L.costs, 8 * b * 4);
+    memcpy(out->status, hbase + L.status, 4 * b);
+    memcpy(out->ok, hbase + L.ok, 4 * b);
+    memcpy(out->attempt, hbase + L.attempt, 4 * b);
+    memcpy(out->nit, hbase + L.nit, 4 * b);
+    memcpy(out->runs, hbase + L.runs, 4 * b);
+    memcpy(out->nfev, hbase + L.nfev, 4 * b);
+    if (out->work) memcpy(out->work, hbase + L.work, 8 * b * 4);
     return NEO_OK;
 }
 
