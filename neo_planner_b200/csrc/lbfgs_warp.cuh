@@ -150,7 +150,7 @@ constexpr int ST_CANCELLED = 7;
 template <int MODE>
 __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
                                    double x0l, OptOut &o, const unsigned *cancel_word = nullptr,
-                                   unsigned cancel_mask = 0u)
+                                   unsigned cancel_mask = 0u, bool lockstep = false)
 {
     const int n = 3 * M - 2;
     const bool mine = lane < n;
@@ -164,6 +164,9 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
     Dcsrch ls;
     o.ns = o.nv = o.nc = 0;
     for (;;) {
+        // Large batches: the warps of a CTA meet here before every evaluation so that they walk through the (~60 KB)
+        // evaluator together and share its instruction fetches (the SM's instruction cache holds 32 KB).
+        if (lockstep) __syncthreads_and(0);
         // ---- the evaluation site: f, g at x (skipped when x is bit-identical to the last evaluated point) ------
         const bool same = !first && __all_sync(FULL, !mine || x == xlast);
         if (!same) {

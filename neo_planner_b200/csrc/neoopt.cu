@@ -28,6 +28,7 @@ constexpr int WARPS_PER_CTA = 4;
 
 struct OptArgs {
     int B, M, max_attempts;
+    int lockstep;                // 1: warps of a CTA synchronise before every evaluation (large batches)
     const double *x0;            // (B,n) tau form
     const int32_t *x0_status;    // (B) or null: NEO_ST_DOMAIN where map_T2tau failed on the host
     const double *head, *tail;   // (B,3,2)
@@ -76,7 +77,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
         unsigned int tid = 0;
         if (lane == 0) tid = atomicAdd(a.counter, 1u);
         tid = __shfl_sync(FULL, tid, 0);
-        if (tid >= total) break;
+        if (tid >= total) {
+            if (a.lockstep) while (!__syncthreads_and(1)) { }      // keep meeting the busy warps until all are idle
+            break;
+        }
         const int at = (int)(tid / (unsigned)a.B);
         const size_t b = tid - (unsigned)at * (unsigned)a.B;
         const unsigned lower_ok = ((1u << at) - 1u) << 8;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(c
             OptOut o;
             o.status = st0; o.nit = 0; o.nfev = 0; o.ns = o.nv = o.nc = 0; o.x = 0.0;
             o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
-            if (!st0) lbfgsb_warp<MODE>(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok);   // else map_T2tau raised (EP:209)
+            if (!st0) lbfgsb_warp<MODE>(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok, a.lockstep != 0);   // else map_T2tau raised (EP:209)
             if (o.status != ST_CANCELLED) {
                 const bool completed = o.status < NEO_ST_OVERFLOW;             // minimize() returned (EP:213-233)
                 const bool accepted = completed && !(o.costs[3] * P.w3 > P.collision_cost_tol);   // EP:235-237
@@ -679,6 +683,10 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.t_info = (int32_t *)(base + o_i); a.p_state = (unsigned *)(base + o_p);
     a.maps = h->d_maps;
     a.counter = h->d_counter;
+    {
+        const char *e = getenv("NEO_LOCKSTEP");      // development override: 0 = never, 1 = always
+        a.lockstep = e ? atoi(e) : 0;
+    }
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
     if (by_piece) k_optimize<SAMPLE_BY_PIECE><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
