@@ -1,0 +1,107 @@
+"""Full-size runs (BASELINE.json configs 4 and 5) checked through size-independent properties, since the CPU checkers
+cannot finish these sizes in test time: determinism, independence of batch composition and order, agreement of the
+speculative retry scheduler with plain sequential semantics, and the invariants every MINCO trajectory must satisfy
+(boundary states, C^4 continuity at the waypoints, durations inside (T_min, T_max), collision tolerance)."""
+import numpy as np
+import pytest
+
+from neo_planner_b200 import guesses, lib
+from neo_planner_b200.worlds import make_world, make_problems, YamlConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def derivs(c, T):
+    """c (B,6,2), T (B,) -> list of the first five derivatives (B,2) of the quintic at T."""
+    out = []
+    for order in range(5):
+        v = np.zeros((c.shape[0], 2))
+        for k in range(order, 6):
+            f = 1.0
+            for q in range(order):
+                f *= (k - q)
+            v += f * c[:, k, :] * (T ** (k - order))[:, None]
+        out.append(v)
+    return out
+
+
+def check_invariants(cfg, M, head, tail, out):
+    ok = out['ok'] == 1
+    c = out['coeffs'][ok].reshape(-1, M, 6, 2); ts = out['ts'][ok]
+    h = lib.pad_state(head)[ok]; t = lib.pad_state(tail)[ok]
+    assert ((ts > cfg.T_min) & (ts < cfg.T_max)).all()
+    scale = 1.0 + np.abs(c).max()
+    # head / tail states (EP:274-279, EP:318-332)
+    assert np.abs(c[:, 0, 0] - h[:, 0]).max() < 1e-9 and np.abs(c[:, 0, 1] - h[:, 1]).max() < 1e-9
+    assert np.abs(2 * c[:, 0, 2] - h[:, 2]).max() < 1e-9
+    end = derivs(c[:, M - 1], ts[:, M - 1])
+    for k in range(3):
+        assert np.abs(end[k] - t[:, k]).max() < 1e-7 * scale
+    # waypoints: position = q_i and continuity of vel, acc, jerk, snap (EP:284-316)
+    x = out['x'][ok]
+    for i in range(M - 1):
+        e = derivs(c[:, i], ts[:, i]); s = derivs(c[:, i + 1], np.zeros(len(ts)))
+        q = np.stack([x[:, i], x[:, (M - 1) + i]], axis=1)
+        assert np.abs(e[0] - q).max() < 1e-7 * scale
+        for k in range(5):
+            assert np.abs(e[k] - s[k]).max() < 1e-6 * scale, (i, k)
+    assert (out['costs'][ok][:, 3] * cfg.weights[3] <= cfg.collision_cost_tol).all()
+    assert (out['nfev'] >= out['runs']).all() and (out['attempt'] < 5).all()
+
+
+def test_config4_65536_problems_256_worlds():
+    cfg = YamlConfig(); M = 3
+    n_worlds, per = 256, 256
+    h = lib.Handle(cfg, 0, n_worlds)
+    heads, tails = [], []
+    for wid in range(n_worlds):
+        w = make_world(wid)
+        h.set_map_occupancy(wid, w.H, w.W, w.res, w.ox, w.oy, w.occ)
+        a, b = make_problems(w, per)
+        heads.append(a); tails.append(b)
+    head = np.concatenate(heads); tail = np.concatenate(tails); ids = np.repeat(np.arange(n_worlds, dtype=np.int32), per)
+    B = len(head)
+    q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
+    rq, rts = guesses.retry_guesses(cfg, head, tail, M, 4, rng=np.random.default_rng(4))
+    out = h.optimize(M, q0, ts0, head, tail, ids, rq, rts, 5)
+    assert out['ok'].mean() > 0.85
+    check_invariants(cfg, M, head, tail, out)
+    # determinism: warps pick tasks in a different order every launch; results must not depend on it
+    again = h.optimize(M, q0, ts0, head, tail, ids, rq, rts, 5)
+    for k in ('x', 'ts', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):
+        assert np.array_equal(out[k], again[k]), k
+    # independence of batch order and composition: a shuffled 4,096-problem subset gives the same per-problem results
+    rng = np.random.default_rng(0)
+    sub = rng.permutation(B)[:4096]
+    part = h.optimize(M, q0[sub], ts0[sub], head[sub], tail[sub], ids[sub], rq[sub], rts, 5)
+    for k in ('x', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):
+        assert np.array_equal(part[k], out[k][sub]), k
+    # speculative retries keep sequential semantics: where attempt 0 is accepted, a 1-attempt run returns the same thing
+    one = h.optimize(M, q0, ts0, head, tail, ids, max_attempts=1)
+    first = out['attempt'] == 0
+    assert first.mean() > 0.7
+    for k in ('x', 'coeffs', 'costs', 'status', 'nit', 'nfev'):
+        assert np.array_equal(one[k][first], out[k][first]), k
+    assert np.array_equal(one['ok'][~first & (out['ok'] == 1)], np.zeros((~first & (out['ok'] == 1)).sum(), np.int32))
+
+
+def test_config5_dense_map_10_pieces():
+    cfg = YamlConfig(); M = 10; cfg.init_wpts_num = M - 1
+    B = 16384
+    w = make_world(0, dense=True)
+    h = lib.Handle(cfg, 0, 1)
+    h.set_map_occupancy(0, w.H, w.W, w.res, w.ox, w.oy, w.occ)
+    head, tail = make_problems(w, B, M=M)
+    q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
+    rq, rts = guesses.retry_guesses(cfg, head, tail, M, 4, rng=np.random.default_rng(5))
+    out = h.optimize(M, q0, ts0, head, tail, None, rq, rts, 5)
+    assert out['ok'].mean() > 0.7
+    check_invariants(cfg, M, head, tail, out)
+    again = h.optimize(M, q0, ts0, head, tail, None, rq, rts, 5)
+    for k in ('x', 'coeffs', 'status', 'ok', 'attempt', 'nit', 'nfev'):
+        assert np.array_equal(out[k], again[k]), k
+    # cost/gradient linearity property of the map lookup: evaluating the returned x reproduces the stored costs on
+    # converged exits (the last evaluated point is the returned one, EP:233)
+    conv = (out['ok'] == 1) & (out['status'] <= 1)
+    ev = h.eval(M, out['x'][conv], head[conv], tail[conv])
+    assert np.allclose(ev['costs'], out['costs'][conv], rtol=1e-9, atol=1e-12)
