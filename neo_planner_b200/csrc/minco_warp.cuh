@@ -91,7 +91,7 @@ __host__ __device__ inline int warp_mem_doubles(int M)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + 15 * 33 + 4 * M + M + 32;
+              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + (M > 4 ? 15 * 33 : 0) + 4 * M + M + 32;
     return (tot + 1) & ~1;
 }
 
@@ -120,7 +120,7 @@ __device__ inline WarpMem carve(double *base, int M)
     m.Y = base; base += HIST * n;
     m.rho = base; base += HIST;
     m.al = base; base += HIST;
-    m.red = base; base += 15 * 33;
+    m.red = base; base += M > 4 ? 15 * 33 : 0;      // only the SAMPLE_ALL_PIECES schedule (M >= 5) stages partial sums
     m.lw = base; base += 2 * M;
     m.pc = base; base += 2 * M;
     m.nsprev = base; base += M;

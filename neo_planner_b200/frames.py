@@ -30,16 +30,19 @@ def rotate_inverse(q, v):
     return np.einsum('...ji,...j->...i', rotation_matrix(q), np.asarray(v, dtype=np.float64))
 
 
-def form_nn_input(depth_img, local_vel, attitude, global_pos, global_vel, des_pos_z, init_pos, init_vel, target_state):
-    """record_planner.py:13-58 for a batch.
-    depth_img (B,H,W) float/uint; local_vel, global_pos, global_vel (B,3); attitude (B,4) wxyz;
-    init_pos/init_vel (B,>=2) planning start in the map frame; target_state (B,2,2) = [pos; vel].
-    Returns depth_norm (B,H,W) uint8 and motion_info (B,24) =
-    [local_vel 3 | R 9 row-major | init pos 3 | init vel 3 | target pos 3 | target vel 3] (body frame)."""
+def normalize_depth(depth_img):
+    """record_planner.py:15: (depth / max(depth) * 255).astype(uint8) per image."""
     depth_img = np.asarray(depth_img)
     B = depth_img.shape[0]
     mx = depth_img.reshape(B, -1).max(axis=1).reshape(B, 1, 1)
-    depth_norm = (depth_img / mx * 255).astype(np.uint8)                      # record_planner.py:15
+    return (depth_img / mx * 255).astype(np.uint8)
+
+
+def motion_info(local_vel, attitude, global_pos, global_vel, des_pos_z, init_pos, init_vel, target_state):
+    """record_planner.py:17-48 for a batch: (B,24) =
+    [local_vel 3 | R 9 row-major | init pos 3 | init vel 3 | target pos 3 | target vel 3] (body frame)."""
+    attitude = np.asarray(attitude, dtype=np.float64)
+    B = attitude.shape[0]
     R = rotation_matrix(attitude)
     p0 = np.zeros((B, 3)); v0 = np.zeros((B, 3))
     p0[:, :2] = np.asarray(init_pos)[:, :2]; p0[:, 2] = des_pos_z
@@ -49,10 +52,18 @@ def form_nn_input(depth_img, local_vel, attitude, global_pos, global_vel, des_po
     tp[:, :2] = target_state[:, 0, :]; tp[:, 2] = des_pos_z
     tv[:, :2] = target_state[:, 1, :]
     gp = np.asarray(global_pos, dtype=np.float64); gv = np.asarray(global_vel, dtype=np.float64)
-    motion = np.concatenate([np.asarray(local_vel, dtype=np.float64), R.reshape(B, 9),
-                             rotate_inverse(attitude, p0 - gp), rotate_inverse(attitude, v0 - gv),
-                             rotate_inverse(attitude, tp - gp), rotate_inverse(attitude, tv - gv)], axis=1)
-    return depth_norm, motion
+    return np.concatenate([np.asarray(local_vel, dtype=np.float64), R.reshape(B, 9),
+                           rotate_inverse(attitude, p0 - gp), rotate_inverse(attitude, v0 - gv),
+                           rotate_inverse(attitude, tp - gp), rotate_inverse(attitude, tv - gv)], axis=1)
+
+
+def form_nn_input(depth_img, local_vel, attitude, global_pos, global_vel, des_pos_z, init_pos, init_vel, target_state):
+    """record_planner.py:13-58 for a batch.
+    depth_img (B,H,W) float/uint; local_vel, global_pos, global_vel (B,3); attitude (B,4) wxyz;
+    init_pos/init_vel (B,>=2) planning start in the map frame; target_state (B,2,2) = [pos; vel].
+    Returns depth_norm (B,H,W) uint8 and motion_info (B,24)."""
+    return normalize_depth(depth_img), motion_info(local_vel, attitude, global_pos, global_vel, des_pos_z, init_pos,
+                                                   init_vel, target_state)
 
 
 def form_nn_output(attitude, global_pos, des_pos_z, int_wpts):

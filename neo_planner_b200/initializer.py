@@ -83,22 +83,43 @@ class NeoBatchPlanner:
             torch.manual_seed(seed)
             net = PlannerNetConv()
         self.net = net.to(self.device).eval()
+        if self.device.type == 'cuda':
+            self.net = self.net.to(memory_format=torch.channels_last)
+
+    @torch.no_grad()
+    def normalize_depth(self, depth_img, chunk=512):
+        """record_planner.py:15 on the device: (depth / max(depth) * 255).astype(uint8), evaluated in fp64 like NumPy
+        does, so the truncation to uint8 is the reference's. depth_img: (B,H,W) array (any real dtype). Returns a uint8
+        CUDA tensor (B,H,W)."""
+        depth_img = np.asarray(depth_img)
+        out = torch.empty(depth_img.shape, dtype=torch.uint8, device=self.device)
+        for i in range(0, len(depth_img), chunk):
+            d = torch.from_numpy(np.ascontiguousarray(depth_img[i:i + chunk])).to(self.device, non_blocking=True).double()
+            mx = d.amax(dim=(1, 2), keepdim=True)
+            out[i:i + chunk] = (d / mx * 255).to(torch.uint8)
+        return out
 
     @torch.no_grad()
     def predict(self, depth_norm, motion_info, chunk=256):
-        x = process_input(depth_norm, motion_info)
+        """Network forward for B samples. depth_norm: (B,H,W) uint8, NumPy or CUDA tensor (images travel as uint8 and
+        are widened on the device; the flattened float vector of nn_trainer.py:51-58 is formed there). Returns (B,9)."""
+        if not torch.is_tensor(depth_norm):
+            depth_norm = torch.from_numpy(np.ascontiguousarray(depth_norm))
+        motion = torch.from_numpy(np.asarray(motion_info, dtype=np.float32)).to(self.device)
+        B = depth_norm.shape[0]
         outs = []
-        for i in range(0, len(x), chunk):
-            xb = torch.from_numpy(x[i:i + chunk]).to(self.device, non_blocking=True)
+        for i in range(0, B, chunk):
+            img = depth_norm[i:i + chunk].to(self.device, non_blocking=True).reshape(-1, IMG_WIDTH * IMG_HEIGHT).float()
+            x = torch.cat([img, motion[i:i + chunk]], dim=1)
             with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.device.type == 'cuda'):
-                outs.append(self.net(xb).float().cpu())
-        return torch.cat(outs).numpy().astype(np.float64)
+                outs.append(self.net(x).float())
+        return torch.cat(outs).double().cpu().numpy()
 
     def enhanced_traj_plan(self, depth_img, local_vel, attitude, global_pos, global_vel, init_pos, init_vel, target_state,
                            map_ids=None, rng=None):
-        depth_norm, motion = frames.form_nn_input(depth_img, local_vel, attitude, global_pos, global_vel, self.des_pos_z,
-                                                  init_pos, init_vel, target_state)
-        out = self.predict(depth_norm, motion)
+        motion = frames.motion_info(local_vel, attitude, global_pos, global_vel, self.des_pos_z, init_pos, init_vel,
+                                    target_state)
+        out = self.predict(self.normalize_depth(depth_img), motion)
         int_wpts, ts = frames.wpts_world(attitude, global_pos, out, M=3)
         head = np.stack([np.asarray(init_pos)[:, :2], np.asarray(init_vel)[:, :2]], axis=1)
         res = self.planner.warm_start_plan(head, target_state, int_wpts, ts, map_ids, rng)
