@@ -286,12 +286,15 @@ def main():
     stream = torch.cuda.Stream(device=dev)     # a real (non-default) stream: NULL would mean "the handle's own stream"
     torch.cuda.set_stream(stream)
 
-    def step_device():
+    def launch_kernel():
         st = torch.cuda.current_stream().cuda_stream
         assert st != 0
         h._ck(h.lib.neo_optimize_dev(h.h, B, M, x0.data_ptr(), None, head.data_ptr(), tail.data_ptr(),
                                      None if ids_d is None else ids_d.data_ptr(), rq.data_ptr(),
                                      rtau_d.data_ptr(), 0, 5, C.byref(res), C.c_void_p(st)))
+
+    def step_device():
+        launch_kernel()
         if distributed:
             dist.all_gather_into_tensor(all_f, out_f)
             dist.all_gather_into_tensor(all_i, out_i)
@@ -319,10 +322,11 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = h.launch_count() - launches0        # kernels of this library launched inside the timed region
-    # keep the GPU under the same load a little longer if the timed region was too short to sample clocks
+    # keep the GPU under the same load a little longer if the timed region was too short to sample clocks.
+    # Kernel launches only: the number of extra iterations differs per rank, so no collective may run here.
     t_extra = time.perf_counter()
     while len(sampler.samples) < 20 and time.perf_counter() - t_extra < 2.0:
-        step_device()
+        launch_kernel()
         torch.cuda.synchronize()
     clocks = sampler.result()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
