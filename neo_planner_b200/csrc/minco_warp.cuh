@@ -211,63 +211,56 @@ __device__ __forceinline__ void load_nodes(const WarpMem &m, int M, int lane, do
     __syncwarp();
 }
 
-// Block-tridiagonal system of the interior nodes (jerk + snap continuity), one lane per node, then block elimination
-// by lanes 0/1 (one per dimension). Leaves D'^-1 in m.blk (reused by the adjoint) and the node (v,a) in m.U.
+// Block-tridiagonal system of the interior nodes (jerk + snap continuity) and its block elimination. Every lane runs
+// the M-1 sequential 2x2 steps for dimension d = lane & 1 with the blocks, right-hand sides and the running inverse in
+// registers (the blocks depend on 1/T^k only; nothing on the dependent chain goes through shared memory). Leaves
+// L, D'^-1, U per node in m.blk (reused by the adjoint) and the node (v, a) in m.U.
 __device__ __forceinline__ void solve_nodes(const WarpMem &m, int M, int lane)
 {
-    if (lane >= 1 && lane < M) {
-        const int j = lane;
-        const double a = m.iT[5 * (j - 1)], a2 = m.iT[5 * (j - 1) + 1], a3 = m.iT[5 * (j - 1) + 2], a4 = m.iT[5 * (j - 1) + 3];
-        const double b = m.iT[5 * j], b2 = m.iT[5 * j + 1], b3 = m.iT[5 * j + 2], b4 = m.iT[5 * j + 3];
-        double *B = m.blk + 12 * j;
-        B[0] = -24.0 * a2; B[1] = -3.0 * a; B[2] = -168.0 * a3; B[3] = -24.0 * a2;                       // L_j
-        B[4] = 36.0 * (b2 - a2); B[5] = 9.0 * (a + b); B[6] = -192.0 * (a3 + b3); B[7] = 36.0 * (a2 - b2);   // D_j
-        B[8] = 24.0 * b2; B[9] = -3.0 * b; B[10] = -168.0 * b3; B[11] = 24.0 * b2;                       // U_j
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            const double dm = m.P[2 * j + d] - m.P[2 * (j - 1) + d], dp = m.P[2 * (j + 1) + d] - m.P[2 * j + d];
-            double r0 = 60.0 * (dp * b3 - dm * a3);
-            double r1 = -360.0 * (dm * a4 + dp * b4);
-            if (j == 1) {           // known (v,a) of the head node
-                const double v = m.U[d], ac = m.U[2 + d];
-                r0 -= B[0] * v + B[1] * ac; r1 -= B[2] * v + B[3] * ac;
-            }
-            if (j == M - 1) {       // known (v,a) of the tail node
-                const double v = m.U[4 * M + d], ac = m.U[4 * M + 2 + d];
-                r0 -= B[8] * v + B[9] * ac; r1 -= B[10] * v + B[11] * ac;
-            }
-            m.r[4 * j + d] = r0; m.r[4 * j + 2 + d] = r1;
+    const int d = lane & 1;
+    const double *__restrict__ iT = m.iT;
+    const double *__restrict__ P = m.P;
+    double *__restrict__ blk = m.blk;
+    double *__restrict__ rr = m.r;
+    double i00 = 0, i01 = 0, i10 = 0, i11 = 0, u00 = 0, u01 = 0, u10 = 0, u11 = 0, p0 = 0, p1 = 0;
+    double a = iT[0], a2 = iT[1], a3 = iT[2], a4 = iT[3];
+    double pm = P[d], pc = P[2 + d];
+    const double hv = m.U[d], ha = m.U[2 + d], tv = m.U[4 * M + d], ta = m.U[4 * M + 2 + d];
+    for (int j = 1; j < M; j++) {
+        const double b = iT[5 * j], b2 = iT[5 * j + 1], b3 = iT[5 * j + 2], b4 = iT[5 * j + 3];
+        const double pn = P[2 * (j + 1) + d];
+        const double l00 = -24.0 * a2, l01 = -3.0 * a, l10 = -168.0 * a3, l11 = l00;                      // L_j
+        double d00 = 36.0 * (b2 - a2), d01 = 9.0 * (a + b), d10 = -192.0 * (a3 + b3), d11 = -d00;         // D_j
+        const double n00 = 24.0 * b2, n01 = -3.0 * b, n10 = -168.0 * b3, n11 = n00;                       // U_j
+        const double dm = pc - pm, dp = pn - pc;
+        double r0 = 60.0 * (dp * b3 - dm * a3), r1 = -360.0 * (dm * a4 + dp * b4);
+        if (j == 1) { r0 -= l00 * hv + l01 * ha; r1 -= l10 * hv + l11 * ha; }          // known (v,a) of the head node
+        if (j == M - 1) { r0 -= n00 * tv + n01 * ta; r1 -= n10 * tv + n11 * ta; }      // known (v,a) of the tail node
+        if (j > 1) {
+            const double w00 = l00 * i00 + l01 * i10, w01 = l00 * i01 + l01 * i11;     // W = L_j D'^-1_{j-1}
+            const double w10 = l10 * i00 + l11 * i10, w11 = l10 * i01 + l11 * i11;
+            d00 -= w00 * u00 + w01 * u10; d01 -= w00 * u01 + w01 * u11;
+            d10 -= w10 * u00 + w11 * u10; d11 -= w10 * u01 + w11 * u11;
+            r0 -= w00 * p0 + w01 * p1; r1 -= w10 * p0 + w11 * p1;
         }
+        const double idet = 1.0 / (d00 * d11 - d01 * d10);
+        i00 = d11 * idet; i01 = -d01 * idet; i10 = -d10 * idet; i11 = d00 * idet;
+        if (lane == 0) {
+            double *B = blk + 12 * j;
+            B[0] = l00; B[1] = l01; B[2] = l10; B[3] = l11;
+            B[4] = i00; B[5] = i01; B[6] = i10; B[7] = i11;
+            B[8] = n00; B[9] = n01; B[10] = n10; B[11] = n11;
+        }
+        if (lane < 2) { rr[4 * j + d] = r0; rr[4 * j + 2 + d] = r1; }
+        u00 = n00; u01 = n01; u10 = n10; u11 = n11; p0 = r0; p1 = r1;
+        a = b; a2 = b2; a3 = b3; a4 = b4; pm = pc; pc = pn;
     }
     __syncwarp();
     {
-        const int d = lane & 1;
-        double i00 = 0, i01 = 0, i10 = 0, i11 = 0, u00 = 0, u01 = 0, u10 = 0, u11 = 0, p0 = 0, p1 = 0;
-        for (int j = 1; j < M; j++) {
-            const double *B = m.blk + 12 * j;
-            double d00 = B[4], d01 = B[5], d10 = B[6], d11 = B[7];
-            double r0 = m.r[4 * j + d], r1 = m.r[4 * j + 2 + d];
-            if (j > 1) {
-                const double l00 = B[0], l01 = B[1], l10 = B[2], l11 = B[3];
-                const double w00 = l00 * i00 + l01 * i10, w01 = l00 * i01 + l01 * i11;     // W = L_j D'^-1_{j-1}
-                const double w10 = l10 * i00 + l11 * i10, w11 = l10 * i01 + l11 * i11;
-                d00 -= w00 * u00 + w01 * u10; d01 -= w00 * u01 + w01 * u11;
-                d10 -= w10 * u00 + w11 * u10; d11 -= w10 * u01 + w11 * u11;
-                r0 -= w00 * p0 + w01 * p1; r1 -= w10 * p0 + w11 * p1;
-            }
-            const double idet = 1.0 / (d00 * d11 - d01 * d10);
-            i00 = d11 * idet; i01 = -d01 * idet; i10 = -d10 * idet; i11 = d00 * idet;
-            u00 = B[8]; u01 = B[9]; u10 = B[10]; u11 = B[11];
-            p0 = r0; p1 = r1;
-            __syncwarp();
-            if (lane == 0) { double *Bw = m.blk + 12 * j; Bw[4] = i00; Bw[5] = i01; Bw[6] = i10; Bw[7] = i11; }
-            if (lane < 2) { m.r[4 * j + d] = r0; m.r[4 * j + 2 + d] = r1; }
-        }
-        __syncwarp();
-        double v = m.U[4 * M + d], ac = m.U[4 * M + 2 + d];
+        double v = tv, ac = ta;
         for (int j = M - 1; j >= 1; j--) {
-            const double *B = m.blk + 12 * j;
-            double r0 = m.r[4 * j + d], r1 = m.r[4 * j + 2 + d];
+            const double *B = blk + 12 * j;
+            double r0 = rr[4 * j + d], r1 = rr[4 * j + 2 + d];
             if (j < M - 1) { r0 -= B[8] * v + B[9] * ac; r1 -= B[10] * v + B[11] * ac; }
             v = B[4] * r0 + B[5] * r1; ac = B[6] * r0 + B[7] * r1;
             if (lane < 2) { m.U[4 * j + d] = v; m.U[4 * j + 2 + d] = ac; }

@@ -65,12 +65,13 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // as soon as an earlier attempt of its problem is accepted. With many problems per SM the queue reaches the retries
 // only when first attempts are finished, so speculation costs nothing; with few problems it halves the tail.
 // The warp whose completion resolves a problem assembles its outputs (final coefficients included).
-template <int MODE>
+// MC: the number of pieces as a compile-time constant (loops over pieces/nodes unroll, lane maps fold).
+template <int MODE, int MC>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int M = a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M, A = a.max_attempts;
+    const int M = MC > 0 ? MC : a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M, A = a.max_attempts;
     const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
     const unsigned total = (unsigned)A * (unsigned)a.B;
     for (;;) {
@@ -181,12 +182,12 @@ struct EvalArgs {
     int32_t *status;
 };
 
-template <int MODE>
+template <int MODE, int MC>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, const EvalArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int M = a.M, n = 3 * M - 2, N = 6 * M;
+    const int M = MC > 0 ? MC : a.M, n = 3 * M - 2, N = 6 * M;
     const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
     for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)a.B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
         begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
@@ -667,8 +668,22 @@ static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm)
 static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 {
     int occ;
-    const bool by_piece = a.M <= 4;       // sampling schedule (minco_warp.cuh): piece by piece for short trajectories
-    int rc = by_piece ? prep_kernel(h, k_optimize<SAMPLE_BY_PIECE>, a.M, &occ) : prep_kernel(h, k_optimize<SAMPLE_ALL_PIECES>, a.M, &occ);
+    // kernel variant: sampling schedule (minco_warp.cuh) by trajectory length; the shipped configuration (M = 3) and
+    // the dense-map configuration (M = 10) get instantiations with the piece count as a compile-time constant
+    void (*kern)(const DevParams, const OptArgs) = nullptr;
+    switch (a.M) {      // one instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
+        case 2: kern = k_optimize<SAMPLE_BY_PIECE, 2>; break;
+        case 3: kern = k_optimize<SAMPLE_BY_PIECE, 3>; break;
+        case 4: kern = k_optimize<SAMPLE_BY_PIECE, 4>; break;
+        case 5: kern = k_optimize<SAMPLE_ALL_PIECES, 5>; break;
+        case 6: kern = k_optimize<SAMPLE_ALL_PIECES, 6>; break;
+        case 7: kern = k_optimize<SAMPLE_ALL_PIECES, 7>; break;
+        case 8: kern = k_optimize<SAMPLE_ALL_PIECES, 8>; break;
+        case 9: kern = k_optimize<SAMPLE_ALL_PIECES, 9>; break;
+        case 10: kern = k_optimize<SAMPLE_ALL_PIECES, 10>; break;
+        default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
+    }
+    int rc = prep_kernel(h, kern, a.M, &occ);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
     const size_t need = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -689,8 +704,7 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     }
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
-    if (by_piece) k_optimize<SAMPLE_BY_PIECE><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
-    else k_optimize<SAMPLE_ALL_PIECES><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
@@ -699,14 +713,25 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
 {
     int occ;
-    const bool by_piece = a.M <= 4;
-    int rc = by_piece ? prep_kernel(h, k_eval<SAMPLE_BY_PIECE>, a.M, &occ) : prep_kernel(h, k_eval<SAMPLE_ALL_PIECES>, a.M, &occ);
+    void (*kern)(const DevParams, const EvalArgs) = nullptr;
+    switch (a.M) {
+        case 2: kern = k_eval<SAMPLE_BY_PIECE, 2>; break;
+        case 3: kern = k_eval<SAMPLE_BY_PIECE, 3>; break;
+        case 4: kern = k_eval<SAMPLE_BY_PIECE, 4>; break;
+        case 5: kern = k_eval<SAMPLE_ALL_PIECES, 5>; break;
+        case 6: kern = k_eval<SAMPLE_ALL_PIECES, 6>; break;
+        case 7: kern = k_eval<SAMPLE_ALL_PIECES, 7>; break;
+        case 8: kern = k_eval<SAMPLE_ALL_PIECES, 8>; break;
+        case 9: kern = k_eval<SAMPLE_ALL_PIECES, 9>; break;
+        case 10: kern = k_eval<SAMPLE_ALL_PIECES, 10>; break;
+        default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
+    }
+    int rc = prep_kernel(h, kern, a.M, &occ);
     if (rc) return rc;
     const int need = (a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
     a.maps = h->d_maps;
-    if (by_piece) k_eval<SAMPLE_BY_PIECE><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
-    else k_eval<SAMPLE_ALL_PIECES><<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
