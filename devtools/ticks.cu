@@ -4,7 +4,8 @@
 #include <cstdio>
 #include <vector>
 using namespace neo;
-__global__ void k_ticks(DevParams P, MapView map, int M, const double *x, const double *ht, long long *ticks, double *out)
+template <int M>
+__global__ void k_ticks(DevParams P, MapView map, const double *x, const double *ht, long long *ticks, double *out)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
@@ -34,7 +35,7 @@ int main()
     double *dx, *dht, *dout; long long *dt;
     cudaMalloc(&dx, sizeof(x)); cudaMalloc(&dht, sizeof(ht)); cudaMalloc(&dout, 64 * 8); cudaMalloc(&dt, 16 * 8);
     cudaMemcpy(dx, x, sizeof(x), cudaMemcpyHostToDevice); cudaMemcpy(dht, ht, sizeof(ht), cudaMemcpyHostToDevice);
-    k_ticks<<<1, 32, sizeof(double) * warp_mem_doubles(M)>>>(P, map, M, dx, dht, dt, dout);
+    k_ticks<3><<<1, 32, sizeof(double) * warp_mem_doubles(M)>>>(P, map, dx, dht, dt, dout);
     long long t[16]; double out[16];
     cudaMemcpy(t, dt, sizeof(t), cudaMemcpyDeviceToHost); cudaMemcpy(out, dout, sizeof(out), cudaMemcpyDeviceToHost);
     printf("err %s f=%g ns=%g\n", cudaGetErrorString(cudaGetLastError()), out[0], out[1]);

@@ -452,7 +452,8 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     double costs2 = 0.0, costs3 = 0.0;
     if (MODE == SAMPLE_BY_PIECE) {
         // few pieces (M <= 4): one piece at a time, lanes over its samples, 16-value butterfly reduction per piece
-        for (int i = 0; i < M; i++) {
+#pragma unroll 1
+        for (int i = 0; i < M; i++) {            // not unrolled: ONE copy of the sample body in the instruction stream
             const int ns = (int)m.nsd[2 * i];                    // int(T/delta_t) (EP:401)
             const double inv_ns = m.nsd[2 * i + 1];
             const double *ci = m.c + 12 * i;
