@@ -19,7 +19,9 @@
  *   reported in `status` arrays (NEO_ST_*), never as a failing return code.
  *   Thread safety: calls on one handle are serialised by an internal mutex; handles are independent.
  *   Functions ending in _dev take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
- *   void*; NULL = the handle's own stream) without synchronising.
+ *   void*; NULL = the handle's own stream) without synchronising. A handle owns ONE set of scratch buffers
+ *   (work-queue counter, per-attempt records): consecutive _dev launches on the same handle must be ordered on the
+ *   same stream, and maps must not be re-uploaded while a launch is in flight. Use one handle per concurrent stream.
  */
 #ifndef NEOOPT_H
 #define NEOOPT_H

@@ -305,3 +305,39 @@ def test_multi_map_slots():
         sl = slice(64 * s, 64 * (s + 1))
         o1 = h1.optimize(3, q0[sl], ts0[sl], head[sl], tail[sl], max_attempts=1)
         assert np.array_equal(o1['x'], out['x'][sl]) and np.array_equal(o1['status'], out['status'][sl])
+
+
+def test_plan_against_scipy_on_unseen_problems():
+    """Problems that are in no fixture: the device path against oracle/minco_ref.py, which runs the REAL scipy L-BFGS-B
+    on the reference's arithmetic (bit-identical to the reference where the fixtures were generated)."""
+    from oracle import minco_ref
+    cfg = YamlConfig(); M = 3
+    w = make_world(21)
+    B = 48
+    head, tail = make_problems(w, B, first=500)
+    q0, ts0 = straight_line_guess(cfg, head, tail, M)
+    rq = np.zeros((B, 4, 2, M - 1))
+    for k in range(B):
+        np.random.seed(9000 + k)
+        rq[k], rts = retry_guesses(cfg, head[k], tail[k], M, 4)
+    h = handle_for(cfg, w)
+    out = h.optimize(M, q0, ts0, head, tail, retry_q=rq, retry_ts=rts, max_attempts=5)
+    grid = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    agree = 0
+    for k in range(B):
+        opt = minco_ref.RefOptimizer(cfg)
+        np.random.seed(9000 + k)
+        try:
+            opt.plan(grid, head[k], tail[k]); ok = 1
+        except Exception:
+            ok = 0
+        if ok != out['ok'][k]:
+            continue
+        if not ok:
+            agree += int(opt.opt_running_times == out['runs'][k])
+            continue
+        c = opt.final_coeffs()
+        agree += int(np.max(np.abs(c - out['coeffs'][k])) <= 1e-4 and opt.iter_num == out['nit'][k]
+                     and opt.opt_running_times == out['runs'][k])
+    print(f'unseen problems vs scipy: {agree}/{B} identical (ok flag, attempts, iterations, coefficients <= 1e-4 m)')
+    assert agree >= 0.9 * B
