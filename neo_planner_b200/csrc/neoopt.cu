@@ -314,6 +314,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    int lockstep = 0;                // development switch (env NEO_LOCKSTEP at neo_create): CTA-level lockstep, see k_optimize
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     char name[128] = {0};
 };
@@ -399,6 +400,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     }
     neo_handle *h = new neo_handle();
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps);
+    if (const char *e = getenv("NEO_LOCKSTEP")) h->lockstep = atoi(e) != 0;
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
     bool good = cudaSetDevice(device) == cudaSuccess &&
@@ -698,10 +700,7 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.t_info = (int32_t *)(base + o_i); a.p_state = (unsigned *)(base + o_p);
     a.maps = h->d_maps;
     a.counter = h->d_counter;
-    {
-        const char *e = getenv("NEO_LOCKSTEP");      // development override: 0 = never, 1 = always
-        a.lockstep = e ? atoi(e) : 0;
-    }
+    a.lockstep = h->lockstep;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
     kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);

@@ -196,3 +196,33 @@ def test_error_behaviour_python_oracle(golden):
     out = c_oracle.plan_batch(p, m, 3, g['head'][:1], g['tail'][:1], q0[None], ts0[None],
                               retry_q=np.repeat(q0[None, None], 4, 1), retry_ts=ts0, max_attempts=5)
     assert out['ok'][0] == 0 and out['runs'][0] == 0 and out['status'][0] == 5
+
+
+@pytest.mark.parametrize('M', [2, 3, 5, 8])
+def test_c_oracle_against_python_oracle_random_points(M):
+    """Beyond the fixtures: the plain-C checker against the Python restatement (bit-identical to the reference where the
+    fixtures were generated) at random decision vectors, random boundary states with accelerations, both parameter sets."""
+    rng = np.random.default_rng(100 + M)
+    w = make_world(9)
+    grid = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    m = c_oracle.OracleMap.from_world(w)
+    for cfg in (YamlConfig(), LibraryDefaultConfig()):
+        cfg.init_wpts_num = M - 1
+        opt = minco_ref.RefOptimizer(cfg)
+        B = 12
+        head = np.zeros((B, 3, 2)); tail = np.zeros((B, 3, 2))
+        head[:, 0] = rng.uniform([2, -6], [20, 6], (B, 2)); head[:, 1] = rng.normal(0, 0.5, (B, 2)); head[:, 2] = rng.normal(0, 0.3, (B, 2))
+        tail[:, 0] = head[:, 0] + rng.uniform([3, -2], [7, 2], (B, 2)); tail[:, 1] = rng.normal(0, 0.5, (B, 2)); tail[:, 2] = rng.normal(0, 0.3, (B, 2))
+        lam = np.linspace(0, 1, M + 1)[1:-1]
+        q = head[:, None, 0, :] + lam[None, :, None] * (tail[:, 0] - head[:, 0])[:, None, :] + rng.normal(0, 0.5, (B, M - 1, 2))
+        tau = rng.normal(0, 1.0, (B, M))
+        x = np.concatenate([np.transpose(q, (0, 2, 1)).reshape(B, -1), tau], axis=1)
+        costs, grad, status = c_oracle.eval_batch(c_oracle.Params.from_config(cfg), m, M, head, tail, x)
+        assert (status == 0).all()
+        wts = np.array(cfg.weights, dtype=float)
+        for k in range(B):
+            opt.set_problem(grid, head[k], tail[k], np.zeros((2, M - 1)), np.ones(M))
+            f = opt.cost(x[k]); c4 = opt.costs.copy(); g = opt.grad(x[k])
+            assert abs(costs[k] @ wts - f) <= 1e-9 * abs(f)
+            assert np.allclose(costs[k], c4, rtol=1e-9, atol=1e-12)
+            assert np.max(np.abs(grad[k] - g)) <= 1e-8 * np.max(np.abs(g)), (M, k)
