@@ -302,30 +302,34 @@ struct EvalOut {
 constexpr int SAMPLE_BY_PIECE = 0;   // M <= 4
 constexpr int SAMPLE_ALL_PIECES = 1; // M >= 5
 
+// Exact quotient (p - origin)/res (ESDF:61-62) for the rare sample whose reciprocal estimate lies within 1e-9 of an
+// integer; kept out of line so the fp64 division sequence does not sit in the hot loop's instruction stream.
+__device__ __noinline__ double exact_quotient(double num, double res) { return num / res; }
+
 // One sample j of one piece (EP:399-466): position/velocity, ESDF lookup, both penalties and their contributions to
 // acc[0..11] = dW/dc (slot 2k+d), acc[12] = dW/dT, acc[13] = feasibility cost, acc[14] = collision cost.
+// Order of work: position -> cell index -> distance load issued, THEN the velocity polynomial and the feasibility term
+// while the load is in flight. Polynomials are evaluated in Estrin form (three independent FMAs, then two dependent
+// ones) instead of a six-deep chain (DFMA latency is 12 cycles on this part).
 __device__ __forceinline__ void sample_point(const DevParams &P, const MapView &map, const double (&cx)[6],
                                              const double (&cy)[6], int j, int ns, double inv_ns, bool want_grad,
                                              double (&acc)[16], EvalOut &out, int &bad)
 {
     const double t = (double)j * P.dt;               // np.arange(0, T_max, dt)[j] (EP:251)
-    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
-    const double px = cx[0] + cx[1] * t + cx[2] * t2 + cx[3] * t3 + cx[4] * t4 + cx[5] * t5;
-    const double py = cy[0] + cy[1] * t + cy[2] * t2 + cy[3] * t3 + cy[4] * t4 + cy[5] * t5;
-    const double b1[6] = {0.0, 1.0, 2.0 * t, 3.0 * t2, 4.0 * t3, 5.0 * t4};
-    const double vx = cx[1] + cx[2] * b1[2] + cx[3] * b1[3] + cx[4] * b1[4] + cx[5] * b1[5];
-    const double vy = cy[1] + cy[2] * b1[2] + cy[3] * b1[3] + cy[4] * b1[4] + cy[5] * b1[5];
-    const double omg = (j == 0 || j == ns - 1) ? 0.5 : 1.0;   // EP:407
+    const double t2 = t * t, t4 = t2 * t2;
+    const double px = fma(t4, fma(cx[5], t, cx[4]), fma(t2, fma(cx[3], t, cx[2]), fma(cx[1], t, cx[0])));
+    const double py = fma(t4, fma(cy[5], t, cy[4]), fma(t2, fma(cy[3], t, cy[2]), fma(cy[1], t, cy[0])));
     // collision lookup (EP:415-417): nearest cell, index = int((p - origin)/res), trunc toward zero (ESDF:61-65).
-    // The quotient is first formed with the reciprocal; the exact IEEE division is only redone when that estimate is
-    // within 1e-9 of an integer, so the truncated index is always the reference's.
+    // The quotient is first formed with the reciprocal (|estimate - exact| <= 4.5e-16 |q| < 1e-9 for every in-map index,
+    // |q| < 2^20); the exact IEEE division is only redone when the estimate is within 1e-9 of an integer, so the
+    // truncated index is always the reference's.
     const double dy = py - map.oy, dx = px - map.ox;
     double fr = dy * map.inv_res, fc = dx * map.inv_res;
     double tr = trunc(fr), tc = trunc(fc);
-    {   // |estimate - exact quotient| <= 4.5e-16 |q| < 1e-9 for every in-map index (|q| < 2^20)
+    {
         const double er = fabs(fr - tr), ec = fabs(fc - tc);
-        if (er < 1e-9 || er > 1.0 - 1e-9) { fr = dy / map.res; tr = trunc(fr); }
-        if (ec < 1e-9 || ec > 1.0 - 1e-9) { fc = dx / map.res; tc = trunc(fc); }
+        if (er < 1e-9 || er > 1.0 - 1e-9) { fr = exact_quotient(dy, map.res); tr = trunc(fr); }
+        if (ec < 1e-9 || ec > 1.0 - 1e-9) { fc = exact_quotient(dx, map.res); tc = trunc(fc); }
     }
     if (fr != fr || fc != fc) bad = 6;                 // int(nan) raises ValueError
     const bool inside = tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W;
@@ -335,16 +339,20 @@ __device__ __forceinline__ void sample_point(const DevParams &P, const MapView &
         cell = map.cells + ((size_t)(int)tr * map.W + (int)tc);
         dis = __ldg(&cell->d);
     }
+    const double t3 = t2 * t;
+    const double b1[6] = {0.0, 1.0, 2.0 * t, 3.0 * t2, 4.0 * t3, 5.0 * t4};
+    const double vx = fma(b1[5], cx[5], fma(b1[4], cx[4], cx[1])) + fma(b1[3], cx[3], b1[2] * cx[2]);
+    const double vy = fma(b1[5], cy[5], fma(b1[4], cy[4], cy[1])) + fma(b1[3], cy[3], b1[2] * cy[2]);
+    const double omg = (j == 0 || j == ns - 1) ? 0.5 : 1.0;   // EP:407
     const double vv = (vx * vx + vy * vy) - P.v_max2;
-    const double vd = P.safe_dis - dis;
     out.ns++;
     if (vv > 0.0) {       // feasibility (EP:409-413, EP:441-451)
         const double vv2 = vv * vv, vv3 = vv2 * vv;
         acc[13] += (omg * P.dt) * vv3;
         if (want_grad) {
             const double K = (3.0 * P.dt * omg) * vv2;
-            const double ax = 2.0 * cx[2] + 6.0 * t * cx[3] + 12.0 * t2 * cx[4] + 20.0 * t3 * cx[5];
-            const double ay = 2.0 * cy[2] + 6.0 * t * cy[3] + 12.0 * t2 * cy[4] + 20.0 * t3 * cy[5];
+            const double ax = fma(20.0 * t3, cx[5], 12.0 * t2 * cx[4]) + fma(6.0 * t, cx[3], 2.0 * cx[2]);
+            const double ay = fma(20.0 * t3, cy[5], 12.0 * t2 * cy[4]) + fma(6.0 * t, cy[3], 2.0 * cy[2]);
             const double v2t = 2.0 * (ax * vx + ay * vy);
             const double kx = (P.w2 * K) * (2.0 * vx), ky = (P.w2 * K) * (2.0 * vy);
 #pragma unroll
@@ -353,6 +361,7 @@ __device__ __forceinline__ void sample_point(const DevParams &P, const MapView &
         }
         out.nv++;
     }
+    const double vd = P.safe_dis - dis;
     if (vd > 0.0) {       // collision (EP:418-422, EP:453-466); outside the map dis = 10000 never violates
         const double vd2 = vd * vd, vd3 = vd2 * vd;
         acc[14] += (omg * P.dt) * vd3;
@@ -361,6 +370,7 @@ __device__ __forceinline__ void sample_point(const DevParams &P, const MapView &
             const double K = (3.0 * P.dt * omg) * vd2;
             const double p2t = -(g.x * vx + g.y * vy);
             const double kx = -(P.w3 * K) * g.x, ky = -(P.w3 * K) * g.y;
+            const double t5 = t4 * t;
             const double b0[6] = {1.0, t, t2, t3, t4, t5};
 #pragma unroll
             for (int k = 0; k < 6; k++) { acc[2 * k] += b0[k] * kx; acc[2 * k + 1] += b0[k] * ky; }
