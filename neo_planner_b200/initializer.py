@@ -85,6 +85,7 @@ class NeoBatchPlanner:
         self.net = net.to(self.device).eval()
         if self.device.type == 'cuda':
             self.net = self.net.to(memory_format=torch.channels_last)
+            torch.backends.cudnn.benchmark = True        # fixed 480x640 frames: let cuDNN pick its fastest kernels once
 
     @torch.no_grad()
     def normalize_depth(self, depth_img, chunk=512):
@@ -100,7 +101,7 @@ class NeoBatchPlanner:
         return out
 
     @torch.no_grad()
-    def predict(self, depth_norm, motion_info, chunk=256):
+    def predict(self, depth_norm, motion_info, chunk=512):
         """Network forward for B samples. depth_norm: (B,H,W) uint8, NumPy or CUDA tensor (images travel as uint8 and
         are widened on the device; the flattened float vector of nn_trainer.py:51-58 is formed there). Returns (B,9)."""
         if not torch.is_tensor(depth_norm):
@@ -109,9 +110,10 @@ class NeoBatchPlanner:
         B = depth_norm.shape[0]
         outs = []
         for i in range(0, B, chunk):
-            img = depth_norm[i:i + chunk].to(self.device, non_blocking=True).reshape(-1, IMG_WIDTH * IMG_HEIGHT).float()
-            x = torch.cat([img, motion[i:i + chunk]], dim=1)
+            img = depth_norm[i:i + chunk].to(self.device, non_blocking=True).reshape(-1, IMG_WIDTH * IMG_HEIGHT)
             with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.device.type == 'cuda'):
+                lowp = self.dtype if self.device.type == 'cuda' else torch.float32      # 0..255 is exact in bf16
+                x = torch.cat([img.to(lowp), motion[i:i + chunk].to(lowp)], dim=1)
                 outs.append(self.net(x).float())
         return torch.cat(outs).double().cpu().numpy()
 

@@ -341,3 +341,28 @@ def test_plan_against_scipy_on_unseen_problems():
                      and opt.opt_running_times == out['runs'][k])
     print(f'unseen problems vs scipy: {agree}/{B} identical (ok flag, attempts, iterations, coefficients <= 1e-4 m)')
     assert agree >= 0.9 * B
+
+
+@pytest.mark.parametrize('M', [3, 6, 10])
+def test_eval_extreme_time_allocations(M, world0):
+    """Durations pushed against both bounds (T_i within 1e-3 of T_min or T_max, ratios up to 10 between neighbours): the
+    un-pivoted block elimination of the node-state system must still agree with the dense pivoted solve of the checker."""
+    cfg = YamlConfig(); cfg.init_wpts_num = M - 1
+    B = 256
+    head, tail = make_problems(world0, B, M=M)
+    q0, ts0 = straight_line_guess(cfg, head, tail, M)
+    rng = np.random.default_rng(50 + M)
+    tau = rng.choice([-8.0, -3.0, 0.0, 3.0, 8.0], size=(B, M)) + rng.normal(0, 0.2, (B, M))
+    x = np.concatenate([q0.reshape(B, -1) + rng.normal(0, 0.3, (B, 2 * (M - 1))), tau], axis=1)
+    h = handle_for(cfg, world0)
+    out = h.eval(M, x, head, tail, want_coeffs=True)
+    m = c_oracle.OracleMap.from_world(world0)
+    costs, grad, status = c_oracle.eval_batch(c_oracle.Params.from_config(cfg), m, M, head, tail, x)
+    assert (status == 0).all() and (out['status'] == 0).all()
+    assert out['ts'].min() < 0.502 and out['ts'].max() > 4.998
+    w = np.array(cfg.weights, dtype=float)
+    f_dev = out['costs'] @ w; f_ref = costs @ w
+    assert np.max(np.abs(f_dev - f_ref) / np.abs(f_ref)) <= 1e-6
+    gerr = np.max(np.abs(out['grad'] - grad), axis=1) / np.max(np.abs(grad), axis=1)
+    print(f'M={M}: extreme T: worst rel cost err {np.max(np.abs(f_dev - f_ref) / np.abs(f_ref)):.2e}, worst rel grad err {gerr.max():.2e}')
+    assert gerr.max() <= 1e-6
