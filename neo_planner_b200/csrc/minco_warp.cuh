@@ -80,7 +80,7 @@ struct WarpMem {
     double *Y;     // [HIST][n]
     double *rho;   // [HIST]
     double *al;    // [HIST]   two-loop recursion coefficients
-    double *red;   // [15][33] per-lane partial sums of the sample loop (padded rows; SAMPLE_ALL_PIECES)
+    double *red;   // [15 or 15*M][33] per-lane partial sums of the sample loop (padded rows)
     double *lw;    // [M][2]   first lane and lane count of each piece (SAMPLE_ALL_PIECES)
     double *pc;    // [M][2]   per-piece feasibility / collision cost
     double *nsprev; // [M]     sample counts the cached lane assignment was computed for (-1: none)
@@ -91,7 +91,7 @@ __host__ __device__ inline int warp_mem_doubles(int M)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + (M > 4 ? 15 * 33 : 0) + 4 * M + M + 32;
+              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + (M > 4 ? 15 * 33 : 15 * 33 * M) + 4 * M + M + 32;
     return (tot + 1) & ~1;
 }
 
@@ -120,7 +120,7 @@ __device__ inline WarpMem carve(double *base, int M)
     m.Y = base; base += HIST * n;
     m.rho = base; base += HIST;
     m.al = base; base += HIST;
-    m.red = base; base += M > 4 ? 15 * 33 : 0;      // only the SAMPLE_ALL_PIECES schedule (M >= 5) stages partial sums
+    m.red = base; base += M > 4 ? 15 * 33 : 15 * 33 * M;   // per-lane partial sums: one block (all-pieces schedule) or one per piece
     m.lw = base; base += 2 * M;
     m.pc = base; base += 2 * M;
     m.nsprev = base; base += M;
@@ -461,7 +461,8 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     // ---- sampled penalties (EP:392-466) -----------------------------------------------------------------
     double costs2 = 0.0, costs3 = 0.0;
     if (MODE == SAMPLE_BY_PIECE) {
-        // few pieces (M <= 4): one piece at a time, lanes over its samples, 16-value butterfly reduction per piece
+        // few pieces (M <= 4): one piece at a time, lanes over its samples; every lane parks its 15 partial sums of the
+        // piece in shared memory (row = (piece, slot), padded to 33 so that the owners below read conflict-free).
 #pragma unroll 1
         for (int i = 0; i < M; i++) {            // not unrolled: ONE copy of the sample body in the instruction stream
             const int ns = (int)m.nsd[2 * i];                    // int(T/delta_t) (EP:401)
@@ -474,16 +475,26 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
 #pragma unroll
             for (int s2 = 0; s2 < 16; s2++) acc[s2] = 0.0;
             for (int j = lane; j < ns; j += 32) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
-            warp_reduce16(acc, lane);
-            const int slot = lane >> 1;
-            const double tot = acc[0];
-            if (!(lane & 1)) {
-                if (slot < 12) m.gC[12 * i + slot] += tot;
-                else if (slot == 12) m.gT[i] += tot;
-            }
-            costs2 += __shfl_sync(FULL, tot, 26);
-            costs3 += __shfl_sync(FULL, tot, 28);
+            double *row = m.red + (15 * i) * 33 + lane;
+#pragma unroll
+            for (int s2 = 0; s2 < 15; s2++) row[s2 * 33] = acc[s2];
         }
+        __syncwarp();
+        // owner o = (piece, slot) adds the 32 per-lane partial sums in lane order (four interleaved chains): uniform
+        // trip counts, no shuffles, deterministic
+        for (int o = lane; o < 15 * M; o += 32) {
+            const double *p = m.red + o * 33;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
+            const double tot = (a0 + a1) + (a2 + a3);
+            const int i = o / 15, s2 = o - 15 * i;
+            if (s2 < 12) m.gC[12 * i + s2] += tot;
+            else if (s2 == 12) m.gT[i] += tot;
+            else m.pc[2 * i + (s2 - 13)] = tot;
+        }
+        __syncwarp();
+        for (int i = 0; i < M; i++) { costs2 += m.pc[2 * i]; costs3 += m.pc[2 * i + 1]; }
     } else {
         // many pieces: the 32 lanes are split among the pieces in proportion to their sample counts (every piece with
         // samples gets at least one lane), so a lane only ever accumulates for ONE piece and all pieces are sampled
