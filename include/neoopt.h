@@ -159,6 +159,28 @@ int neo_get_coeffs(neo_handle *h, int B, int M, const double *q, const double *t
 int neo_sample(neo_handle *h, int B, int M, const double *coeffs, const double *ts, double hz, int max_samples,
                double *states, int32_t *count);
 
+/* geometric initializer ---------------------------------------------------------------------------- */
+/* AstarPlanner.plan (astar_planner.py:22-103) followed by GeoPlanner.prune_path_nodes (geo_planner.py:57-101) for B
+ * start/target pairs, one warp each: 8-connected A* over the map grid enlarged by int(10 m / res) cells (origin moved by
+ * -5 m), nodes tested with ESDF.has_collision (0.5 m), open-set ties resolved like Python's min() over the insertion-
+ * ordered dict; then line-of-sight shortcutting (0.1 m samples, 0.4 m clearance) and selection of exactly four key
+ * nodes, of which the middle two are the int_wpts GeoPlanner.geo_traj_plan warm-starts from (geo_planner.py:29).
+ * start, target (B,2); map_ids (B) or NULL. Outputs: pruned (B,4,2); path_len (B) full path length; path
+ * (B,max_path,2) or NULL: the first min(path_len, max_path) path nodes [x, y]; closed (B) number of expanded nodes;
+ * status (B): NEO_ASTAR_FOUND, NEO_ASTAR_EXHAUSTED (open set ran empty: path = [target cell], as the reference returns),
+ * NEO_ASTAR_START_OUTSIDE (start not on the enlarged grid; the reference's grid index would alias -- rejected here),
+ * NEO_ASTAR_LIMIT (more than max_closed > 0 nodes expanded; 0 = no limit, the reference has none). */
+#define NEO_ASTAR_FOUND 0
+#define NEO_ASTAR_EXHAUSTED 1
+#define NEO_ASTAR_START_OUTSIDE 2
+#define NEO_ASTAR_LIMIT 3
+int neo_astar(neo_handle *h, int B, const double *start, const double *target, const int32_t *map_ids, int max_closed,
+              int max_path, double *path, int32_t *path_len, double *pruned, int32_t *status, int32_t *closed);
+/* Device-pointer variant, enqueued on `stream` and not synchronised (scratch is grown before the launch). */
+int neo_astar_dev(neo_handle *h, int B, const double *start, const double *target, const int32_t *map_ids,
+                  int max_closed, int max_path, double *path, int32_t *path_len, double *pruned, int32_t *status,
+                  int32_t *closed, void *stream);
+
 /* measurement helpers ---------------------------------------------------------------------------- */
 /* Device time in ms of the most recent optimize/eval kernel launched through a host-pointer entry point
  * (CUDA events on the launching stream). */

@@ -1,0 +1,398 @@
+// astar_warp.cuh -- the reference's geometric initializer on a warp:
+//   AP  = src/planner/scripts/traj_planner/astar_planner.py  (AstarPlanner.plan, AP:22-103)
+//   GEO = src/planner/scripts/traj_planner/geo_planner.py    (seg_feasible_check GEO:41-55, prune_path_nodes GEO:57-101)
+// One warp per start/target pair. The search is sequential by nature (one node is closed at a time and the choice
+// depends on everything before it), so the warp parallelises what the reference does inside one step: the scan of the
+// open set for the first minimum of g + h in insertion order (AP:62, a Python min() over a dict), the eight neighbour
+// tests (AP:76-95) and the sampled line-of-sight checks of the pruning pass. Results are identical to the reference:
+// same closed order, same parents, same path, same four key nodes.
+//
+// Per-warp scratch in HBM (dense over the enlarged grid, 24 B per cell): node records {g, parent, tag}, the open list
+// (swap-remove) and the insertion list (used to wipe exactly the touched records afterwards and, later, as the key-node
+// list). With 400 x 400 search cells that is 3.8 MB per warp; the working set of one search (a few thousand records)
+// stays in L1/L2.
+//
+// The same source runs with a single lane on the host (devtools/astar_host.cu) -- a development aid used to check the
+// logic against oracle/astar_ref.py in the GPU-less build container; the library never calls it.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "minco_warp.cuh"
+
+namespace neo {
+
+struct AstarNode {
+    double g;       // cost from the start (AP:77)
+    int parent;     // grid index of the parent, -1 for the start (AP:16)
+    int tag;        // 0 untouched, n > 0: open, n-th node ever inserted (dict order of AP:55), -n: closed
+};
+
+enum { ASTAR_FOUND = 0, ASTAR_EXHAUSTED = 1, ASTAR_START_OUTSIDE = 2, ASTAR_LIMIT = 3 };
+
+#define NEO_HD __host__ __device__ __forceinline__
+
+// ---- lane primitives: 32 lanes on the device, 1 lane in the host build ---------------------------------------------
+NEO_HD int a_lanes()
+{
+#ifdef __CUDA_ARCH__
+    return 32;
+#else
+    return 1;
+#endif
+}
+NEO_HD int a_lane()
+{
+#ifdef __CUDA_ARCH__
+    return threadIdx.x & 31;
+#else
+    return 0;
+#endif
+}
+NEO_HD void a_sync()
+{
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
+}
+NEO_HD unsigned a_ballot(bool p)
+{
+#ifdef __CUDA_ARCH__
+    return __ballot_sync(0xffffffffu, p);
+#else
+    return p ? 1u : 0u;
+#endif
+}
+NEO_HD int a_popc(unsigned v)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+NEO_HD int a_from_lane0(int v)
+{
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(0xffffffffu, v, 0);
+#else
+    return v;
+#endif
+}
+// IEEE operations without contraction (the reference is Python float arithmetic)
+NEO_HD double a_add(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+NEO_HD double a_sub(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+NEO_HD double a_mul(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+NEO_HD double a_div(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+NEO_HD double a_sqrt(double a)
+{
+#ifdef __CUDA_ARCH__
+    return __dsqrt_rn(a);
+#else
+    return sqrt(a);
+#endif
+}
+// lexicographic minimum of (f, tag) over the warp; tags are unique, so every lane ends with the same triple
+NEO_HD void a_argmin(double &f, int &tag, int &k)
+{
+#ifdef __CUDA_ARCH__
+    for (int o = 16; o > 0; o >>= 1) {
+        const double f2 = __shfl_xor_sync(0xffffffffu, f, o);
+        const int t2 = __shfl_xor_sync(0xffffffffu, tag, o);
+        const int k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        if (f2 < f || (f2 == f && t2 < tag)) { f = f2; tag = t2; k = k2; }
+    }
+#endif
+}
+
+// ESDF.get_edt_dis (ESDF:53-67): nearest-cell read, 10000 outside the map, Python int() truncation
+NEO_HD double a_dist(const MapView &map, double x, double y)
+{
+    const double tr = trunc(a_div(a_sub(y, map.oy), map.res));
+    const double tc = trunc(a_div(a_sub(x, map.ox), map.res));
+    if (!(tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W)) return 10000.0;
+    return map.cells[(size_t)(int)tr * map.W + (int)tc].d;
+}
+
+// numpy.linspace(a, b, n)[i] (float64, endpoint=True): i * step + a with two roundings, the last sample is b itself
+NEO_HD double a_linspace(double a, double b, int n, int i)
+{
+    if (n > 1 && i == n - 1) return b;
+    if (n <= 1) return a;
+    const double delta = a_sub(b, a), div = (double)(n - 1);
+    const double step = a_div(delta, div);
+    if (step == 0.0) return a_add(a_mul(a_div((double)i, div), delta), a);
+    return a_add(a_mul((double)i, step), a);
+}
+
+// search-grid geometry of one map (AP:31-41)
+struct AstarGrid {
+    int W, H;
+    double ox, oy;
+};
+NEO_HD AstarGrid astar_grid(const MapView &map)
+{
+    AstarGrid g;
+    const int pad = (int)a_div(10.0, map.res);      // int(map_expand_radius / resolution)
+    g.W = map.W + pad; g.H = map.H + pad;
+    g.ox = a_sub(map.ox, 5.0); g.oy = a_sub(map.oy, 5.0);
+    return g;
+}
+inline size_t astar_grid_cells(int H, int W, double res)
+{
+    const int pad = (int)(10.0 / res);
+    return (size_t)(W + pad) * (size_t)(H + pad);
+}
+
+// GEO:41-55: every sample of the segment keeps 0.4 m clearance
+NEO_HD bool a_segment_clear(const MapView &map, double x0, double y0, double x1, double y1)
+{
+    const int lane = a_lane(), NL = a_lanes();
+    const double m = fmax(fabs(a_sub(x1, x0)), fabs(a_sub(y1, y0)));
+    const int n = (int)ceil(a_div(m, 0.1)) + 1;
+    bool bad = false;
+    for (int i = lane; i < n; i += NL)
+        if (a_dist(map, a_linspace(x0, x1, n, i), a_linspace(y0, y1, n, i)) < 0.4) bad = true;
+    return a_ballot(bad) == 0u;
+}
+
+// One start/target pair, executed by one warp (all lanes call with the same arguments).
+//   nodes/open/order: this warp's scratch, nodes all-zero on entry and restored to all-zero on exit.
+//   path_out (max_path, 2) may be NULL; path_len is the full length even when it exceeds max_path.
+NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *order, const double *start,
+                          const double *target, int max_closed, int max_path, double *path_out, int32_t *path_len_out,
+                          double *pruned_out, int32_t *status_out, int32_t *closed_out)
+{
+    const int lane = a_lane(), NL = a_lanes();
+    const unsigned lt = (1u << lane) - 1u;
+    const AstarGrid g = astar_grid(map);
+    const double res = map.res;
+    const double SQRT2 = 1.4142135623730951;                     // math.sqrt(2) (AP:111-114)
+
+    // AP:119-120 (and Node.__init__'s int()): truncation toward zero
+    const double fsx = trunc(a_div(a_sub(start[0], g.ox), res)), fsy = trunc(a_div(a_sub(start[1], g.oy), res));
+    const double ftx = trunc(a_div(a_sub(target[0], g.ox), res)), fty = trunc(a_div(a_sub(target[1], g.oy), res));
+    const double BIG = 1.0e9;
+    int status = ASTAR_FOUND;
+    if (!(fsx >= 0.0 && fsx < (double)g.W && fsy >= 0.0 && fsy < (double)g.H)) status = ASTAR_START_OUTSIDE;
+    // a target far outside the grid can never be reached; clamp only so that index differences stay in range
+    const int tx = (int)fmin(fmax(ftx, -BIG), BIG), ty = (int)fmin(fmax(fty, -BIG), BIG);
+    int n_open = 0, n_seen = 0, n_closed = 0, t_parent = -1;
+
+    if (status == ASTAR_FOUND) {
+        const int sx = (int)fsx, sy = (int)fsy;
+        const int s_idx = sx + sy * g.W;                          // AP:122-124
+        if (lane == 0) {
+            AstarNode s; s.g = 0.0; s.parent = -1; s.tag = 1;
+            nodes[s_idx] = s; open[0] = s_idx; order[0] = s_idx;
+        }
+        n_open = 1; n_seen = 1;
+        a_sync();
+        for (;;) {
+            if (n_open == 0) { status = ASTAR_EXHAUSTED; break; }            // AP:58-60
+            // AP:62: first minimum of cost + hypot in dict (insertion) order
+            double bf = INFINITY; int bt = 0x7fffffff, bk = -1;
+            for (int k = lane; k < n_open; k += NL) {
+                const int idx = open[k];
+                const AstarNode c = nodes[idx];
+                const long long dx = (long long)(idx % g.W) - tx, dy = (long long)(idx / g.W) - ty;
+                const double f = a_add(c.g, a_sqrt((double)(dx * dx + dy * dy)));
+                if (f < bf || (f == bf && c.tag < bt)) { bf = f; bt = c.tag; bk = k; }
+            }
+            a_argmin(bf, bt, bk);
+            const int cur = open[bk];
+            const int cx = cur % g.W, cy = cur / g.W;
+            const double cg = nodes[cur].g;
+            if (cx == tx && cy == ty) { t_parent = nodes[cur].parent; break; }  // AP:66-69
+            a_sync();
+            if (lane == 0) { open[bk] = open[n_open - 1]; nodes[cur].tag = -bt; }   // AP:72-73
+            n_open--; n_closed++;
+            a_sync();
+            if (max_closed > 0 && n_closed > max_closed) { status = ASTAR_LIMIT; break; }
+            // AP:76-95: the eight moves, insertion order = move order
+            for (int base = 0; base < 8; base += NL) {
+                const int mv = base + lane;
+                bool fresh = false; int nidx = 0; double ng = 0.0;
+                if (mv < 8) {
+                    // moves (1,0) (0,1) (-1,0) (0,-1) (-1,-1) (-1,1) (1,-1) (1,1): (d + 1) packed two bits per move
+                    const int nx = cx + (int)((0xA046u >> (2 * mv)) & 3u) - 1;
+                    const int ny = cy + (int)((0x8819u >> (2 * mv)) & 3u) - 1;
+                    if (nx >= 0 && nx < g.W && ny >= 0 && ny < g.H) {
+                        nidx = nx + ny * g.W;
+                        const AstarNode c = nodes[nidx];
+                        if (c.tag >= 0) {                                             // AP:83
+                            const double px = a_add(g.ox, a_mul((double)nx, res));    // AP:116-117
+                            const double py = a_add(g.oy, a_mul((double)ny, res));
+                            if (!(a_dist(map, px, py) < 0.5)) {                       // has_collision (ESDF:50-51)
+                                ng = a_add(cg, mv < 4 ? 1.0 : SQRT2);
+                                if (c.tag == 0) fresh = true;                         // AP:91-92
+                                else if (c.g > ng) { nodes[nidx].g = ng; nodes[nidx].parent = cur; }   // AP:94-95
+                            }
+                        }
+                    }
+                }
+                const unsigned b = a_ballot(fresh);
+                if (fresh) {
+                    const int r = a_popc(b & lt);
+                    AstarNode nn; nn.g = ng; nn.parent = cur; nn.tag = n_seen + r + 1;
+                    nodes[nidx] = nn; open[n_open + r] = nidx; order[n_seen + r] = nidx;
+                }
+                n_open += a_popc(b); n_seen += a_popc(b);
+            }
+            a_sync();
+        }
+    }
+
+    // AP:143-151: [target cell] + closed parents, reversed. chain[] (in the open list's storage) holds the parents.
+    int *chain = open;
+    int n_chain = 0;
+    if (status == ASTAR_FOUND && lane == 0) {
+        int p = t_parent;
+        while (p != -1) { chain[n_chain++] = p; p = nodes[p].parent; }
+    }
+    n_chain = a_from_lane0(n_chain);
+    a_sync();
+    for (int k = lane; k < n_seen; k += NL) { AstarNode z; z.g = 0.0; z.parent = 0; z.tag = 0; nodes[order[k]] = z; }
+    const int L = (status == ASTAR_FOUND || status == ASTAR_EXHAUSTED) ? n_chain + 1 : 0;
+
+#define NEO_PATH_XY(i, X, Y)                                                                              \
+    do {                                                                                                  \
+        int ix_, iy_;                                                                                     \
+        if ((i) < n_chain) { const int c_ = chain[n_chain - 1 - (i)]; ix_ = c_ % g.W; iy_ = c_ / g.W; }   \
+        else { ix_ = tx; iy_ = ty; }                                                                      \
+        X = a_add(g.ox, a_mul((double)ix_, res)); Y = a_add(g.oy, a_mul((double)iy_, res));               \
+    } while (0)
+
+    if (path_out)
+        for (int i = lane; i < L && i < max_path; i += NL) {
+            double x, y;
+            NEO_PATH_XY(i, x, y);
+            path_out[2 * i] = x; path_out[2 * i + 1] = y;
+        }
+
+    // GEO:61-75: greedy shortcutting; key indices go to keys[] (the insertion list's storage, free again)
+    int *keys = order;
+    int nk = 0;
+    a_sync();
+    if (L > 0) {
+        if (lane == 0) keys[0] = 0;
+        nk = 1;
+        int head = 0, tail = 1;
+        while (tail < L) {
+            double hx, hy;
+            NEO_PATH_XY(head, hx, hy);
+            for (;;) {
+                double qx, qy;
+                NEO_PATH_XY(tail, qx, qy);
+                if (!(a_segment_clear(map, hx, hy, qx, qy) || tail - head == 1)) break;
+                tail++;
+                if (tail == L) break;
+            }
+            if (lane == 0) keys[nk] = tail - 1;
+            nk++;
+            head = tail - 1;
+        }
+    }
+    a_sync();
+
+    // GEO:78-95: exactly four key nodes
+    int pick[4] = {0, 0, 0, 0};
+    if (nk == 2) {
+        const double k0 = (double)keys[0], k1 = (double)keys[1];
+        pick[0] = (int)a_linspace(k0, k1, 4, 0); pick[1] = (int)a_linspace(k0, k1, 4, 1);
+        pick[2] = (int)a_linspace(k0, k1, 4, 2); pick[3] = (int)a_linspace(k0, k1, 4, 3);
+    } else if (nk == 3) {
+        const int k0 = keys[0], k1 = keys[1], k2 = keys[2];
+        if (k1 - k0 > k2 - k1) { pick[0] = k0; pick[1] = (k0 + k1) / 2; pick[2] = k1; pick[3] = k2; }
+        else { pick[0] = k0; pick[1] = k1; pick[2] = (k1 + k2) / 2; pick[3] = k2; }
+    } else if (nk == 4) {
+        for (int i = 0; i < 4; i++) pick[i] = keys[i];
+    } else if (nk > 0) {
+        const int last = keys[nk - 1];
+        const double left = a_mul(a_div(1.0, 3.0), (double)last), right = a_mul(a_div(2.0, 3.0), (double)last);
+        int il = keys[0], ir = keys[0];
+        double dl = fabs(a_sub((double)il, left)), dr = fabs(a_sub((double)ir, right));
+        for (int i = 1; i < nk; i++) {
+            const int v = keys[i];
+            const double el = fabs(a_sub((double)v, left)), er = fabs(a_sub((double)v, right));
+            if (el < dl) { dl = el; il = v; }
+            if (er < dr) { dr = er; ir = v; }
+        }
+        pick[0] = keys[0]; pick[1] = il; pick[2] = ir; pick[3] = last;
+    }
+    if (lane == 0) {
+        for (int i = 0; i < 4; i++) {
+            double x = 0.0, y = 0.0;
+            if (L > 0) NEO_PATH_XY(pick[i], x, y);
+            pruned_out[2 * i] = x; pruned_out[2 * i + 1] = y;
+        }
+        *path_len_out = L; *status_out = status; *closed_out = n_closed;
+    }
+#undef NEO_PATH_XY
+    a_sync();
+}
+
+#ifdef __CUDACC__
+// persistent warps; warp w owns scratch block w
+struct AstarArgs {
+    const MapView *maps;
+    const int32_t *map_ids;      // (B) or NULL
+    const double *start, *target;   // (B,2)
+    int B, max_closed, max_path;
+    double *path;                // (B,max_path,2) or NULL
+    int32_t *path_len, *status, *closed;
+    double *pruned;              // (B,4,2)
+    AstarNode *nodes; int *open; int *order;
+    size_t cap;                  // scratch cells per warp
+    unsigned int *counter;
+};
+
+__global__ void __launch_bounds__(128) k_astar(const AstarArgs a)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    AstarNode *nodes = a.nodes + (size_t)warp * a.cap;
+    int *open = a.open + (size_t)warp * a.cap;
+    int *order = a.order + (size_t)warp * a.cap;
+    for (;;) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(a.counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned)a.B) break;
+        const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
+        astar_problem(map, nodes, open, order, a.start + 2 * (size_t)b, a.target + 2 * (size_t)b, a.max_closed, a.max_path,
+                      a.path ? a.path + (size_t)b * a.max_path * 2 : nullptr, a.path_len + b, a.pruned + 8 * (size_t)b,
+                      a.status + b, a.closed + b);
+    }
+}
+#endif
+
+}  // namespace neo

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/neoopt.h"
+#include "astar_warp.cuh"
 #include "lbfgs_warp.cuh"
 #include "map_kernels.cuh"
 #include "minco_warp.cuh"
@@ -310,6 +311,9 @@ struct neo_handle {
     unsigned int *d_counter = nullptr;
     std::vector<DevBuf> bufs;        // reusable device staging buffers for the host-pointer entry points
     DevBuf pinned;                   // reusable pinned host staging buffer (neo_optimize)
+    DevBuf astar;                    // per-warp search scratch of neo_astar (node records all-zero between launches)
+    size_t astar_cap = 0;            // cells per warp the scratch is laid out for
+    int astar_warps = 0;             // worker warps the scratch is laid out for
     std::string err;
     std::mutex mu;
     float last_ms = 0.f;
@@ -426,6 +430,7 @@ extern "C" int neo_destroy(neo_handle *h)
     for (auto &s : h->slots) { if (s.cells) cudaFree(s.cells); if (s.occ) cudaFree(s.occ); }
     for (auto &b : h->bufs) if (b.p) cudaFree(b.p);
     if (h->pinned.p) cudaFreeHost(h->pinned.p);
+    if (h->astar.p) cudaFree(h->astar.p);
     cudaFree(h->d_maps); cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -1044,6 +1049,125 @@ extern "C" int neo_sample(neo_handle *h, int B, int M, const double *coeffs, con
         if (states) CK(cudaMemcpyAsync(states, d_s, sizeof(double) * b * ms * 6, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (states) for (size_t i = 0; i < b; i++) if (count[i] > max_samples) return fail(h, "neo_sample: max_samples too small");
+    }
+    return NEO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// geometric initializer (astar_warp.cuh)
+// ---------------------------------------------------------------------------------------------------------
+constexpr size_t ASTAR_SCRATCH_BUDGET = (size_t)8 << 30;     // bytes of HBM the per-warp search scratch may take
+constexpr int ASTAR_WARPS_PER_SM = 16;
+
+static int astar_launch(neo_handle *h, int B, const double *start, const double *target, const int32_t *map_ids,
+                        int max_closed, int max_path, double *path, int32_t *path_len, double *pruned, int32_t *status,
+                        int32_t *closed, cudaStream_t st)
+{
+    // scratch: one dense block per worker warp, sized for the largest enlarged grid among the uploaded maps
+    size_t cap = 0;
+    for (auto &s : h->slots)
+        if (s.cells) { const size_t c = astar_grid_cells(s.H, s.W, s.res); cap = c > cap ? c : cap; }
+    if (cap == 0) return fail(h, "neo_astar: no map uploaded");
+    if (cap > (size_t)0x7fffffff) return fail(h, "neo_astar: search grid too large for 32-bit cell indices");
+    const size_t per_warp = cap * (sizeof(AstarNode) + 2 * sizeof(int));
+    size_t warps = (size_t)h->sm_count * ASTAR_WARPS_PER_SM;
+    if (warps > ASTAR_SCRATCH_BUDGET / per_warp) warps = ASTAR_SCRATCH_BUDGET / per_warp;
+    if (warps > (size_t)B) warps = B;
+    if (warps < 1) warps = 1;
+    warps = (warps + 3) / 4 * 4;                                // whole CTAs of 4 warps
+    if (h->astar_cap != cap || (size_t)h->astar_warps < warps) {
+        if (h->astar.p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(h->astar.p)); h->astar.p = nullptr; }
+        h->astar_cap = 0; h->astar_warps = 0;
+        CK(cudaMalloc(&h->astar.p, per_warp * warps));
+        CK(cudaMemsetAsync(h->astar.p, 0, sizeof(AstarNode) * cap * warps, st));
+        h->astar_cap = cap; h->astar_warps = (int)warps;
+    }
+    AstarArgs a;
+    a.maps = h->d_maps; a.map_ids = map_ids; a.start = start; a.target = target;
+    a.B = B; a.max_closed = max_closed; a.max_path = max_path;
+    a.path = path; a.path_len = path_len; a.status = status; a.closed = closed; a.pruned = pruned;
+    const size_t laid = (size_t)h->astar_warps;                 // the layout follows the allocation, not this launch
+    a.nodes = (AstarNode *)h->astar.p;
+    a.open = (int *)((char *)h->astar.p + sizeof(AstarNode) * cap * laid);
+    a.order = a.open + cap * laid;
+    a.cap = cap;
+    a.counter = h->d_counter + 16;
+    CK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+    k_astar<<<(unsigned)(warps / 4), 128, 0, st>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return NEO_OK;
+}
+
+static int astar_check(neo_handle *h, int B, const double *start, const double *target, int max_closed, int max_path,
+                       const double *path, const int32_t *path_len, const double *pruned, const int32_t *status,
+                       const int32_t *closed)
+{
+    if (B < 0 || max_closed < 0 || max_path < 0) return fail(h, "neo_astar: invalid argument");
+    if (!start || !target || !path_len || !pruned || !status || !closed || (path && max_path < 1))
+        return fail(h, "neo_astar: null pointer");
+    return NEO_OK;
+}
+
+extern "C" int neo_astar_dev(neo_handle *h, int B, const double *start, const double *target, const int32_t *map_ids,
+                             int max_closed, int max_path, double *path, int32_t *path_len, double *pruned,
+                             int32_t *status, int32_t *closed, void *stream)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = astar_check(h, B, start, target, max_closed, max_path, path, path_len, pruned, status, closed);
+    if (rc) return rc;
+    if (B == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    return astar_launch(h, B, start, target, map_ids, max_closed, max_path, path, path_len, pruned, status, closed,
+                        stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int neo_astar(neo_handle *h, int B, const double *start, const double *target, const int32_t *map_ids,
+                         int max_closed, int max_path, double *path, int32_t *path_len, double *pruned, int32_t *status,
+                         int32_t *closed)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = astar_check(h, B, start, target, max_closed, max_path, path, path_len, pruned, status, closed);
+    if (rc) return rc;
+    if (B == 0) return NEO_OK;
+    for (int i = 0; i < 2 * B; i++)
+        if (!isfinite(start[i]) || !isfinite(target[i])) return fail(h, "neo_astar: start/target must be finite");
+    if (map_ids)
+        for (int i = 0; i < B; i++)
+            if (map_ids[i] < 0 || map_ids[i] >= (int)h->slots.size() || !h->slots[map_ids[i]].cells)
+                return fail(h, "neo_astar: map id refers to an empty slot");
+    if (!map_ids && !h->slots[0].cells) return fail(h, "neo_astar: slot 0 is empty");
+    CK(cudaSetDevice(h->device));
+    const size_t b = B, np = path ? (size_t)max_path : 0;
+    for (int pass = 0; pass < 2; pass++) {
+        Carver c{pass ? (char *)h->bufs[7].p : nullptr};
+        double *d_s = c.take<double>(2 * b), *d_t = c.take<double>(2 * b), *d_pr = c.take<double>(8 * b),
+               *d_path = c.take<double>(2 * b * np + 1);
+        int32_t *d_ids = c.take<int32_t>(b), *d_len = c.take<int32_t>(b), *d_st = c.take<int32_t>(b),
+                *d_cl = c.take<int32_t>(b);
+        if (!pass) {
+            void *p;
+            if ((rc = dev_buf(h, 7, c.off + 256, &p))) return rc;
+            continue;
+        }
+        cudaStream_t st = h->stream;
+        CK(cudaMemcpyAsync(d_s, start, sizeof(double) * 2 * b, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_t, target, sizeof(double) * 2 * b, cudaMemcpyHostToDevice, st));
+        if (map_ids) CK(cudaMemcpyAsync(d_ids, map_ids, sizeof(int32_t) * b, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(h->ev0, st));
+        rc = astar_launch(h, B, d_s, d_t, map_ids ? d_ids : nullptr, max_closed, max_path, path ? d_path : nullptr, d_len,
+                          d_pr, d_st, d_cl, st);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev1, st));
+        CK(cudaMemcpyAsync(path_len, d_len, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(closed, d_cl, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pruned, d_pr, sizeof(double) * 8 * b, cudaMemcpyDeviceToHost, st));
+        if (path) CK(cudaMemcpyAsync(path, d_path, sizeof(double) * 2 * b * np, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     }
     return NEO_OK;
 }

@@ -15,6 +15,7 @@ MAX_ATTEMPTS = 8
 ST_CONV_FTOL, ST_CONV_PG, ST_ABNORMAL, ST_MAXITER, ST_OVERFLOW, ST_DOMAIN, ST_NAN = range(7)
 STATUS_NAMES = ['CONV_FTOL', 'CONV_PG', 'ABNORMAL', 'MAXITER', 'OVERFLOW', 'DOMAIN', 'NAN']
 ERR_NO_DEVICE = -3
+ASTAR_FOUND, ASTAR_EXHAUSTED, ASTAR_START_OUTSIDE, ASTAR_LIMIT = range(4)
 
 
 class NeoError(RuntimeError):
@@ -45,7 +46,7 @@ class Result(C.Structure):
 EXPORTS = ['neo_create', 'neo_destroy', 'neo_set_config', 'neo_last_error', 'neo_device_info', 'neo_set_map_esdf',
            'neo_set_map_occupancy', 'neo_set_map_points', 'neo_get_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
            'neo_optimize_dev', 'neo_T2tau', 'neo_get_coeffs', 'neo_sample', 'neo_last_kernel_ms', 'neo_fp64_peak',
-           'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host']
+           'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host', 'neo_astar', 'neo_astar_dev']
 
 _lib = None
 
@@ -83,6 +84,8 @@ def load():
         lib.neo_launch_count.argtypes = [V, V]
         lib.neo_test_exp_dev.argtypes = [V, I, V, V]
         lib.neo_test_exp_host.argtypes = [I, V, V]
+        lib.neo_astar.argtypes = [V, I, V, V, V, I, I, V, V, V, V, V]
+        lib.neo_astar_dev.argtypes = [V, I, V, V, V, I, I, V, V, V, V, V, V]
         _lib = lib
     return _lib
 
@@ -248,6 +251,21 @@ class Handle:
         states = np.zeros((B, mx, 3, 2))
         self._ck(self.lib.neo_sample(self.h, B, M, ptr(coeffs), ptr(ts), float(hz), mx, ptr(states), ptr(count)))
         return states, count
+
+    # ---- geometric initializer -------------------------------------------------------------------------
+    def astar(self, start, target, map_ids=None, max_path=0, max_closed=0):
+        """neo_astar: A* + pruning for B start/target pairs -> dict(pruned (B,4,2), path_len, status, closed[, path])."""
+        start = f64(start).reshape(-1, 2); B = start.shape[0]
+        target = f64(target, (B, 2))
+        ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        pruned = np.zeros((B, 4, 2)); plen = np.zeros(B, np.int32); st = np.zeros(B, np.int32); cl = np.zeros(B, np.int32)
+        path = np.zeros((B, max_path, 2)) if max_path > 0 else None
+        self._ck(self.lib.neo_astar(self.h, B, ptr(start), ptr(target), ptr(ids), int(max_closed), int(max_path), ptr(path),
+                                    ptr(plen), ptr(pruned), ptr(st), ptr(cl)))
+        out = dict(pruned=pruned, path_len=plen, status=st, closed=cl)
+        if path is not None:
+            out['path'] = path
+        return out
 
     # ---- measurement -----------------------------------------------------------------------------------
     def last_kernel_ms(self):

@@ -52,6 +52,7 @@ class _MapCache:
     def __init__(self, handle):
         self.handle = handle
         self.keys = {}
+        self.held = {}      # the cached object itself: keeps its id() from being reused by a new map while it is the key
 
     def ensure(self, slot, m):
         key = (id(m), getattr(m, 'version', None), id(getattr(m, 'esdf_map', None)))
@@ -65,6 +66,7 @@ class _MapCache:
         else:
             raise TypeError('map must expose esdf_map/esdf_grad_x/esdf_grad_y (ESDF) or be a worlds.World')
         self.keys[slot] = key
+        self.held[slot] = (m, getattr(m, 'esdf_map', None))
 
 
 class TrajUtils:

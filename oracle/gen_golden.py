@@ -287,6 +287,79 @@ def gen_errors(name):
     print(name, outcome, pl.opt_running_times, pl2.opt_running_times)
 
 
+def gen_geo(name):
+    """§8f rank 4: AstarPlanner.plan (astar_planner.py:22-103) + GeoPlanner.prune_path_nodes / geo_traj_plan
+    (geo_planner.py:19-101) from the unmodified reference. astar_planner imports matplotlib (absent here) only for its
+    unused visualize_path helper, so an empty stand-in module is registered before the import."""
+    import types
+    from types import SimpleNamespace as NS
+    for mod in ('matplotlib', 'matplotlib.pyplot'):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    from astar_planner import AstarPlanner  # noqa: E402  (reference)
+    from geo_planner import GeoPlanner  # noqa: E402  (reference)
+    from oracle import astar_ref
+    cfg = cfg_for(3)
+    sets = []
+    for world_id, dense, Mlen, n in ((0, False, 3, 24), (0, False, 10, 16), (2, False, 10, 8), (1, True, 10, 4)):
+        w = make_world(world_id, dense=dense)
+        e = ref_map(w)
+        g = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+        head, tail = make_problems(w, n, M=Mlen)
+        sets.append((world_id, dense, w, e, g, head, tail))
+    wid = []; dns = []; heads = []; tails = []; paths = []; plen = []; pruned = []
+    P_ok = []; P_x = []; P_ts = []; P_iter = []; P_runs = []; n_keys = []
+    for world_id, dense, w, e, g, head, tail in sets:
+        for i in range(head.shape[0]):
+            ap = AstarPlanner()
+            path = ap.plan(e, head[i, 0], tail[i, 0])
+            gp = GeoPlanner(cfg)
+            four = gp.prune_path_nodes(e, path)
+            mine, found, _ = astar_ref.astar(g, head[i, 0], tail[i, 0])
+            assert found and mine == path, (world_id, i)
+            if len(path) < 80:
+                assert astar_ref.astar_plain(g, head[i, 0], tail[i, 0]) == path
+            four2, pick, keys = astar_ref.prune(g, path)
+            assert four2 == four, (world_id, i)
+            n_keys.append(len(keys))
+            wid.append(world_id); dns.append(int(dense)); heads.append(head[i]); tails.append(tail[i])
+            paths.append(np.array(path)); plen.append(len(path)); pruned.append(np.array(four))
+            # the full geometric warm start (GEO:19-39) with reproducible retry noise
+            if not dense:
+                st = NS(global_pos=np.array([head[i, 0, 0], head[i, 0, 1], 2.0]),
+                        global_vel=np.array([head[i, 1, 0], head[i, 1, 1], 0.0]))
+                gp = GeoPlanner(cfg)
+                np.random.seed(100 + i)
+                try:
+                    with quiet():
+                        gp.geo_traj_plan(e, st, tail[i])
+                    P_ok.append(1); P_x.append(np.concatenate((gp.int_wpts.reshape(-1), gp.tau))); P_ts.append(gp.ts)
+                except Exception:
+                    P_ok.append(0); P_x.append(np.zeros(7)); P_ts.append(np.zeros(3))
+                P_iter.append(gp.iter_num); P_runs.append(gp.opt_running_times)
+            else:
+                P_ok.append(-1); P_x.append(np.zeros(7)); P_ts.append(np.zeros(3)); P_iter.append(0); P_runs.append(0)
+    # an unreachable target (inside a pillar): the reference exhausts the grid and returns [target cell] (AP:58-60).
+    # Only feasible to run on a tiny map, the reference's open-set scan is quadratic.
+    occ = np.zeros((12, 16), np.int8); occ[5:8, 9:12] = 100
+    tiny = NS(info=NS(resolution=1.0, width=16, height=12, origin=NS(position=NS(x=0.0, y=0.0))), data=occ.reshape(-1))
+    et = ESDF(); et.occupancy_map_cb(tiny)
+    ap = AstarPlanner()
+    with quiet():
+        lost = ap.plan(et, [2.5, 2.5], [10.5, 6.5])
+    gt = minco_ref.GridMap(occ, 12, 16, 1.0, 0.0, 0.0)
+    mine, found, nclosed = astar_ref.astar(gt, [2.5, 2.5], [10.5, 6.5])
+    assert not found and mine == lost
+    lost_four = GeoPlanner(cfg).prune_path_nodes(et, lost)
+    assert astar_ref.prune(gt, lost)[0] == lost_four
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, world_id=np.array(wid), dense=np.array(dns),
+                        head=np.array(heads), tail=np.array(tails), path=np.concatenate(paths), path_len=np.array(plen),
+                        pruned=np.array(pruned), n_keys=np.array(n_keys), plan_ok=np.array(P_ok), plan_x=np.array(P_x),
+                        plan_ts=np.array(P_ts), plan_iter=np.array(P_iter), plan_runs=np.array(P_runs),
+                        tiny_occ=occ, lost_path=np.array(lost), lost_pruned=np.array(lost_four), lost_closed=nclosed)
+    print(name, 'paths', len(plen), 'len', min(plen), max(plen), 'key-node counts', sorted(set(n_keys)),
+          'geo plans ok', sum(1 for v in P_ok if v == 1), '/', sum(1 for v in P_ok if v >= 0))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     gen_esdf()
@@ -297,3 +370,4 @@ if __name__ == '__main__':
     gen_plans(10, 24, 'plans_M10.npz')
     gen_batch_plan(16, 'batch_plan_M3.npz')
     gen_errors('errors.npz')
+    gen_geo('geo_M3.npz')

@@ -174,3 +174,26 @@ def test_initializer_network_shapes():
         assert y.shape == (2, 9) and torch.isfinite(y).all()
     n_params = sum(p.numel() for p in initializer.PlannerNet().parameters())
     assert 11_000_000 < n_params < 12_000_000          # ResNet-18 trunk (1-channel stem) + the small heads
+
+
+def test_map_cache_reuploads_a_new_map_object():
+    """The upload cache is keyed on the map object's identity; a map that is garbage-collected must not hand its id() to
+    the next one unnoticed (the cache holds a reference to what it cached)."""
+    from types import SimpleNamespace as NS
+    from neo_planner_b200.planner import _MapCache
+
+    class FakeHandle:
+        def __init__(self):
+            self.uploads = []
+
+        def set_map_occupancy(self, slot, H, W, res, ox, oy, occ):
+            self.uploads.append((slot, int(np.asarray(occ).sum())))
+
+    fh = FakeHandle()
+    cache = _MapCache(fh)
+    for k in range(6):                       # temporaries: each is freed before the next is created
+        cache.ensure(0, NS(occ=np.full((4, 4), k, np.int8), H=4, W=4, res=1.0, ox=0.0, oy=0.0))
+    assert [u[1] for u in fh.uploads] == [16 * k for k in range(6)]
+    m = NS(occ=np.zeros((4, 4), np.int8), H=4, W=4, res=1.0, ox=0.0, oy=0.0)
+    cache.ensure(0, m); cache.ensure(0, m)
+    assert len(fh.uploads) == 7

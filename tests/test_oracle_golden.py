@@ -226,3 +226,47 @@ def test_c_oracle_against_python_oracle_random_points(M):
             assert abs(costs[k] @ wts - f) <= 1e-9 * abs(f)
             assert np.allclose(costs[k], c4, rtol=1e-9, atol=1e-12)
             assert np.max(np.abs(grad[k] - g)) <= 1e-8 * np.max(np.abs(g)), (M, k)
+
+
+# ---- geometric initializer: oracle/astar_ref.py against the reference's A* + pruning ----------
+def _geo_cases(g):
+    """(world_id, dense) -> GridMap, built once per map of the fixture."""
+    from neo_planner_b200.worlds import make_world
+    maps = {}
+    for wid, dn in sorted(set(zip(g['world_id'].tolist(), g['dense'].tolist()))):
+        w = make_world(wid, dense=bool(dn))
+        maps[(wid, dn)] = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    return maps
+
+
+def test_astar_oracle_matches_reference_paths(golden):
+    from oracle import astar_ref
+    g = golden('geo_M3.npz')
+    maps = _geo_cases(g)
+    off = np.concatenate(([0], np.cumsum(g['path_len'])))
+    plain_checked = 0
+    for i in range(len(g['path_len'])):
+        gm = maps[(int(g['world_id'][i]), int(g['dense'][i]))]
+        ref_path = g['path'][off[i]:off[i + 1]]
+        path, found, _ = astar_ref.astar(gm, g['head'][i, 0], g['tail'][i, 0])
+        assert found and np.array_equal(np.array(path), ref_path), i
+        four, pick, keys = astar_ref.prune(gm, path)
+        assert np.array_equal(np.array(four), g['pruned'][i]) and len(keys) == g['n_keys'][i], i
+        if len(path) < 60 and plain_checked < 6:      # the reference's own dict + min() formulation selects the same nodes
+            assert astar_ref.astar_plain(gm, g['head'][i, 0], g['tail'][i, 0]) == path
+            plain_checked += 1
+        iw, ts, _ = astar_ref.geo_guess(gm, g['head'][i, 0], g['tail'][i, 0], 2.5) if i < 4 else (None, None, None)
+        if iw is not None:
+            assert np.array_equal(iw, g['pruned'][i, 1:3].T) and list(ts) == [3.75, 2.5, 3.75]
+    assert plain_checked >= 3 and set(g['n_keys'].tolist()) >= {2, 3, 4, 5}
+
+
+def test_astar_oracle_unreachable_target(golden):
+    """AP:58-60: an exhausted open set returns the target cell alone; pruning pads it to four copies (GEO:90-95)."""
+    from oracle import astar_ref
+    g = golden('geo_M3.npz')
+    gm = minco_ref.GridMap(g['tiny_occ'], 12, 16, 1.0, 0.0, 0.0)
+    path, found, nclosed = astar_ref.astar(gm, [2.5, 2.5], [10.5, 6.5])
+    assert not found and np.array_equal(np.array(path), g['lost_path']) and nclosed == int(g['lost_closed'])
+    assert np.array_equal(np.array(astar_ref.prune(gm, path)[0]), g['lost_pruned'])
+    assert astar_ref.astar_plain(gm, [2.5, 2.5], [10.5, 6.5]) == path
