@@ -7,10 +7,12 @@
 // tests (AP:76-95) and the sampled line-of-sight checks of the pruning pass. Results are identical to the reference:
 // same closed order, same parents, same path, same four key nodes.
 //
-// Per-warp scratch in HBM (dense over the enlarged grid, 24 B per cell): node records {g, parent, tag}, the open list
-// (swap-remove) and the insertion list (used to wipe exactly the touched records afterwards and, later, as the key-node
-// list). With 400 x 400 search cells that is 3.8 MB per warp; the working set of one search (a few thousand records)
-// stays in L1/L2.
+// The open list {f, g, cell, insertion number} lives in shared memory (512 entries per warp, structure of arrays; longer
+// lists spill to HBM), so the scan of every step reads on-chip data only and f is computed once per insertion/update.
+// Per-warp scratch in HBM (dense over the enlarged grid, 36 B per cell): node records {parent, state/open position}, the
+// insertion list (used to wipe exactly the touched records afterwards and, later, as the key-node list) and the spill
+// area of the open list. With 400 x 400 search cells that is 5.8 MB per warp, of which one search touches a few thousand
+// records.
 //
 // The same source runs with a single lane on the host (devtools/astar_host.cu) -- a development aid used to check the
 // logic against oracle/astar_ref.py in the GPU-less build container; the library never calls it.
@@ -24,9 +26,24 @@
 namespace neo {
 
 struct AstarNode {
-    double g;       // cost from the start (AP:77)
     int parent;     // grid index of the parent, -1 for the start (AP:16)
-    int tag;        // 0 untouched, n > 0: open, n-th node ever inserted (dict order of AP:55), -n: closed
+    int state;      // 0 untouched, -1 closed (AP:72-73), k + 1: open, stored at position k of the open list
+};
+
+// One open node (AP:55 `open_set`). f = g + hypot is kept up to date with g, so the scan for the minimum reads f and, on
+// ties, the insertion number only.
+struct OpenRec {
+    double f, g;
+    int xy, tag;    // node x | y << 16; tag = n-th node ever inserted (the dict order the reference's min() resolves ties by)
+};
+
+// The open list: positions [0, cap) live in shared memory (structure of arrays, conflict-free scans), positions beyond
+// that spill to this warp's block in HBM. Removal swaps the last entry into the hole.
+struct OpenList {
+    double *f, *g;
+    int *xy, *tag;
+    int cap;
+    OpenRec *spill;
 };
 
 enum { ASTAR_FOUND = 0, ASTAR_EXHAUSTED = 1, ASTAR_START_OUTSIDE = 2, ASTAR_LIMIT = 3 };
@@ -121,16 +138,21 @@ NEO_HD double a_sqrt(double a)
     return sqrt(a);
 #endif
 }
-// lexicographic minimum of (f, tag) over the warp; tags are unique, so every lane ends with the same triple
+// lexicographic minimum of (f, tag) over the warp; f >= 0, so its bit pattern orders like an unsigned integer and three
+// 32-bit warp reductions (high word, low word, tag) replace five rounds of 64-bit shuffles. Tags are unique: one winner.
 NEO_HD void a_argmin(double &f, int &tag, int &k)
 {
 #ifdef __CUDA_ARCH__
-    for (int o = 16; o > 0; o >>= 1) {
-        const double f2 = __shfl_xor_sync(0xffffffffu, f, o);
-        const int t2 = __shfl_xor_sync(0xffffffffu, tag, o);
-        const int k2 = __shfl_xor_sync(0xffffffffu, k, o);
-        if (f2 < f || (f2 == f && t2 < tag)) { f = f2; tag = t2; k = k2; }
-    }
+    const unsigned FULL = 0xffffffffu;
+    const unsigned hi = (unsigned)__double2hiint(f), lo = (unsigned)__double2loint(f);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    const bool cand = hi == mh && lo == ml;
+    const unsigned mt = __reduce_min_sync(FULL, cand ? (unsigned)tag : 0xffffffffu);
+    const int src = __ffs(__ballot_sync(FULL, cand && (unsigned)tag == mt)) - 1;
+    f = __hiloint2double((int)mh, (int)ml);
+    tag = (int)mt;
+    k = __shfl_sync(FULL, k, src);
 #endif
 }
 
@@ -173,6 +195,15 @@ inline size_t astar_grid_cells(int H, int W, double res)
     return (size_t)(W + pad) * (size_t)(H + pad);
 }
 
+// AP:130-132 for one node of the enlarged grid: map.has_collision(calc_real_pos(ix, iy)). Evaluated once per map into
+// MapView::blocked (k_astar_blocked), so the search reads one byte per neighbour instead of two divisions and a cell.
+NEO_HD bool astar_blocked_at(const MapView &map, const AstarGrid &g, int ix, int iy)
+{
+    const double px = a_add(g.ox, a_mul((double)ix, map.res));       // AP:116-117
+    const double py = a_add(g.oy, a_mul((double)iy, map.res));
+    return a_dist(map, px, py) < 0.5;                                // ESDF:50-51
+}
+
 // GEO:41-55: every sample of the segment keeps 0.4 m clearance
 NEO_HD bool a_segment_clear(const MapView &map, double x0, double y0, double x1, double y1)
 {
@@ -185,10 +216,23 @@ NEO_HD bool a_segment_clear(const MapView &map, double x0, double y0, double x1,
     return a_ballot(bad) == 0u;
 }
 
+// open-list accessors (position k: shared memory below cap, HBM above)
+NEO_HD OpenRec ol_get(const OpenList &o, int k)
+{
+    if (k >= o.cap) return o.spill[k - o.cap];
+    OpenRec r; r.f = o.f[k]; r.g = o.g[k]; r.xy = o.xy[k]; r.tag = o.tag[k];
+    return r;
+}
+NEO_HD void ol_put(const OpenList &o, int k, const OpenRec &r)
+{
+    if (k >= o.cap) { o.spill[k - o.cap] = r; return; }
+    o.f[k] = r.f; o.g[k] = r.g; o.xy[k] = r.xy; o.tag[k] = r.tag;
+}
+
 // One start/target pair, executed by one warp (all lanes call with the same arguments).
-//   nodes/open/order: this warp's scratch, nodes all-zero on entry and restored to all-zero on exit.
+//   nodes/order/ol.spill: this warp's scratch in HBM; nodes all-zero on entry and restored to all-zero on exit.
 //   path_out (max_path, 2) may be NULL; path_len is the full length even when it exceeds max_path.
-NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *order, const double *start,
+NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const OpenList ol, const double *start,
                           const double *target, int max_closed, int max_path, double *path_out, int32_t *path_len_out,
                           double *pruned_out, int32_t *status_out, int32_t *closed_out)
 {
@@ -208,12 +252,16 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *o
     const int tx = (int)fmin(fmax(ftx, -BIG), BIG), ty = (int)fmin(fmax(fty, -BIG), BIG);
     int n_open = 0, n_seen = 0, n_closed = 0, t_parent = -1;
 
+#define NEO_HYPOT(X, Y) a_sqrt((double)(((long long)(X) - tx) * ((long long)(X) - tx) + ((long long)(Y) - ty) * ((long long)(Y) - ty)))
+
     if (status == ASTAR_FOUND) {
         const int sx = (int)fsx, sy = (int)fsy;
         const int s_idx = sx + sy * g.W;                          // AP:122-124
         if (lane == 0) {
-            AstarNode s; s.g = 0.0; s.parent = -1; s.tag = 1;
-            nodes[s_idx] = s; open[0] = s_idx; order[0] = s_idx;
+            OpenRec r; r.g = 0.0; r.f = a_add(0.0, NEO_HYPOT(sx, sy)); r.xy = sx | (sy << 16); r.tag = 1;
+            ol_put(ol, 0, r);
+            AstarNode s; s.parent = -1; s.state = 1;
+            nodes[s_idx] = s; order[0] = s_idx;
         }
         n_open = 1; n_seen = 1;
         a_sync();
@@ -221,41 +269,50 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *o
             if (n_open == 0) { status = ASTAR_EXHAUSTED; break; }            // AP:58-60
             // AP:62: first minimum of cost + hypot in dict (insertion) order
             double bf = INFINITY; int bt = 0x7fffffff, bk = -1;
-            for (int k = lane; k < n_open; k += NL) {
-                const int idx = open[k];
-                const AstarNode c = nodes[idx];
-                const long long dx = (long long)(idx % g.W) - tx, dy = (long long)(idx / g.W) - ty;
-                const double f = a_add(c.g, a_sqrt((double)(dx * dx + dy * dy)));
-                if (f < bf || (f == bf && c.tag < bt)) { bf = f; bt = c.tag; bk = k; }
+            const int n_fast = n_open < ol.cap ? n_open : ol.cap;
+            for (int k = lane; k < n_fast; k += NL) {
+                const double f = ol.f[k];
+                const int t = ol.tag[k];
+                if (f < bf || (f == bf && t < bt)) { bf = f; bt = t; bk = k; }
+            }
+            for (int k = ol.cap + lane; k < n_open; k += NL) {
+                const OpenRec r = ol.spill[k - ol.cap];
+                if (r.f < bf || (r.f == bf && r.tag < bt)) { bf = r.f; bt = r.tag; bk = k; }
             }
             a_argmin(bf, bt, bk);
-            const int cur = open[bk];
-            const int cx = cur % g.W, cy = cur / g.W;
-            const double cg = nodes[cur].g;
+            const OpenRec cur_rec = ol_get(ol, bk);
+            const int cx = cur_rec.xy & 0xffff, cy = cur_rec.xy >> 16;
+            const int cur = cx + cy * g.W;
+            const double cg = cur_rec.g;
             if (cx == tx && cy == ty) { t_parent = nodes[cur].parent; break; }  // AP:66-69
             a_sync();
-            if (lane == 0) { open[bk] = open[n_open - 1]; nodes[cur].tag = -bt; }   // AP:72-73
+            if (lane == 0) {                                                     // AP:72-73
+                const int last = n_open - 1;
+                if (bk != last) { const OpenRec mv = ol_get(ol, last); ol_put(ol, bk, mv); nodes[(mv.xy & 0xffff) + (mv.xy >> 16) * g.W].state = bk + 1; }
+                nodes[cur].state = -1;
+            }
             n_open--; n_closed++;
             a_sync();
             if (max_closed > 0 && n_closed > max_closed) { status = ASTAR_LIMIT; break; }
             // AP:76-95: the eight moves, insertion order = move order
             for (int base = 0; base < 8; base += NL) {
                 const int mv = base + lane;
-                bool fresh = false; int nidx = 0; double ng = 0.0;
+                bool fresh = false; int nidx = 0, nxy = 0; double ng = 0.0, nf = 0.0;
                 if (mv < 8) {
                     // moves (1,0) (0,1) (-1,0) (0,-1) (-1,-1) (-1,1) (1,-1) (1,1): (d + 1) packed two bits per move
                     const int nx = cx + (int)((0xA046u >> (2 * mv)) & 3u) - 1;
                     const int ny = cy + (int)((0x8819u >> (2 * mv)) & 3u) - 1;
                     if (nx >= 0 && nx < g.W && ny >= 0 && ny < g.H) {
-                        nidx = nx + ny * g.W;
+                        nidx = nx + ny * g.W; nxy = nx | (ny << 16);
                         const AstarNode c = nodes[nidx];
-                        if (c.tag >= 0) {                                             // AP:83
-                            const double px = a_add(g.ox, a_mul((double)nx, res));    // AP:116-117
-                            const double py = a_add(g.oy, a_mul((double)ny, res));
-                            if (!(a_dist(map, px, py) < 0.5)) {                       // has_collision (ESDF:50-51)
-                                ng = a_add(cg, mv < 4 ? 1.0 : SQRT2);
-                                if (c.tag == 0) fresh = true;                         // AP:91-92
-                                else if (c.g > ng) { nodes[nidx].g = ng; nodes[nidx].parent = cur; }   // AP:94-95
+                        const bool blk = map.blocked[nidx] != 0;                      // has_collision at this node
+                        if (c.state >= 0 && !blk) {                                   // AP:83, AP:86
+                            ng = a_add(cg, mv < 4 ? 1.0 : SQRT2);
+                            nf = a_add(ng, NEO_HYPOT(nx, ny));
+                            if (c.state == 0) fresh = true;                           // AP:91-92
+                            else {                                                    // AP:94-95
+                                OpenRec r = ol_get(ol, c.state - 1);
+                                if (r.g > ng) { r.g = ng; r.f = nf; ol_put(ol, c.state - 1, r); nodes[nidx].parent = cur; }
                             }
                         }
                     }
@@ -263,17 +320,20 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *o
                 const unsigned b = a_ballot(fresh);
                 if (fresh) {
                     const int r = a_popc(b & lt);
-                    AstarNode nn; nn.g = ng; nn.parent = cur; nn.tag = n_seen + r + 1;
-                    nodes[nidx] = nn; open[n_open + r] = nidx; order[n_seen + r] = nidx;
+                    OpenRec nr; nr.f = nf; nr.g = ng; nr.xy = nxy; nr.tag = n_seen + r + 1;
+                    ol_put(ol, n_open + r, nr);
+                    AstarNode nn; nn.parent = cur; nn.state = n_open + r + 1;
+                    nodes[nidx] = nn; order[n_seen + r] = nidx;
                 }
                 n_open += a_popc(b); n_seen += a_popc(b);
             }
             a_sync();
         }
     }
+#undef NEO_HYPOT
 
-    // AP:143-151: [target cell] + closed parents, reversed. chain[] (in the open list's storage) holds the parents.
-    int *chain = open;
+    // AP:143-151: [target cell] + closed parents, reversed. chain[] (in the open list's HBM part) holds the parents.
+    int *chain = (int *)ol.spill;
     int n_chain = 0;
     if (status == ASTAR_FOUND && lane == 0) {
         int p = t_parent;
@@ -281,7 +341,7 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *o
     }
     n_chain = a_from_lane0(n_chain);
     a_sync();
-    for (int k = lane; k < n_seen; k += NL) { AstarNode z; z.g = 0.0; z.parent = 0; z.tag = 0; nodes[order[k]] = z; }
+    for (int k = lane; k < n_seen; k += NL) { AstarNode z; z.parent = 0; z.state = 0; nodes[order[k]] = z; }
     const int L = (status == ASTAR_FOUND || status == ASTAR_EXHAUSTED) ? n_chain + 1 : 0;
 
 #define NEO_PATH_XY(i, X, Y)                                                                              \
@@ -363,6 +423,11 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *open, int *o
 
 #ifdef __CUDACC__
 // persistent warps; warp w owns scratch block w
+constexpr int ASTAR_OPEN_FAST = 512;     // open-list positions per warp held in shared memory (24 B each)
+constexpr int ASTAR_WARPS_PER_CTA = 4;
+constexpr size_t ASTAR_SMEM_BYTES = (size_t)ASTAR_WARPS_PER_CTA * ASTAR_OPEN_FAST * 24;
+constexpr size_t ASTAR_BYTES_PER_CELL = sizeof(AstarNode) + sizeof(int) + sizeof(OpenRec);
+
 struct AstarArgs {
     const MapView *maps;
     const int32_t *map_ids;      // (B) or NULL
@@ -371,16 +436,31 @@ struct AstarArgs {
     double *path;                // (B,max_path,2) or NULL
     int32_t *path_len, *status, *closed;
     double *pruned;              // (B,4,2)
-    AstarNode *nodes; int *open; int *order;
+    AstarNode *nodes; int *order; OpenRec *spill;     // per-warp blocks of `cap` entries each
     size_t cap;                  // scratch cells per warp
     unsigned int *counter;
 };
 
-__global__ void __launch_bounds__(128) k_astar(const AstarArgs a)
+// one thread per node of the enlarged grid (map.blocked itself is not read)
+__global__ void k_astar_blocked(const MapView map, unsigned char *__restrict__ out)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const AstarGrid g = astar_grid(map);
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y;
+    if (ix < g.W && iy < g.H) out[(size_t)iy * g.W + ix] = astar_blocked_at(map, g, ix, iy) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(ASTAR_WARPS_PER_CTA * 32) k_astar(const AstarArgs a)
+{
+    extern __shared__ __align__(16) unsigned char astar_smem[];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wc = threadIdx.x >> 5;
+    OpenList ol;
+    ol.cap = ASTAR_OPEN_FAST;
+    ol.f = (double *)astar_smem + (size_t)wc * 2 * ASTAR_OPEN_FAST;
+    ol.g = ol.f + ASTAR_OPEN_FAST;
+    ol.xy = (int *)((double *)astar_smem + (size_t)ASTAR_WARPS_PER_CTA * 2 * ASTAR_OPEN_FAST) + (size_t)wc * 2 * ASTAR_OPEN_FAST;
+    ol.tag = ol.xy + ASTAR_OPEN_FAST;
+    ol.spill = a.spill + (size_t)warp * a.cap;
     AstarNode *nodes = a.nodes + (size_t)warp * a.cap;
-    int *open = a.open + (size_t)warp * a.cap;
     int *order = a.order + (size_t)warp * a.cap;
     for (;;) {
         unsigned int b = 0;
@@ -388,7 +468,7 @@ __global__ void __launch_bounds__(128) k_astar(const AstarArgs a)
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= (unsigned)a.B) break;
         const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-        astar_problem(map, nodes, open, order, a.start + 2 * (size_t)b, a.target + 2 * (size_t)b, a.max_closed, a.max_path,
+        astar_problem(map, nodes, order, ol, a.start + 2 * (size_t)b, a.target + 2 * (size_t)b, a.max_closed, a.max_path,
                       a.path ? a.path + (size_t)b * a.max_path * 2 : nullptr, a.path_len + b, a.pruned + 8 * (size_t)b,
                       a.status + b, a.closed + b);
     }

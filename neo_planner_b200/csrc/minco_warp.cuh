@@ -55,6 +55,7 @@ struct MapView {
     int H, W;
     double res, ox, oy;
     double inv_res;
+    const unsigned char *blocked;   // astar_warp.cuh: has_collision at every node of the enlarged search grid (1 = blocked)
 };
 
 // Per-warp shared-memory slice (all doubles). n = 3M-2 decision variables.

@@ -26,6 +26,9 @@ constexpr int WARPS_PER_CTA = 4;
 #ifndef NEO_MIN_CTAS
 #define NEO_MIN_CTAS 2
 #endif
+#ifndef NEO_PACKED_MIN_PER_SM
+#define NEO_PACKED_MIN_PER_SM 324    // problems x pieces per SM from which the 3-CTAs-per-SM instantiation is launched
+#endif                               // (measured break-even: M = 3 near 16 k problems, M = 10 near 4 k, scripts/gpu_ab_min_ctas.py)
 
 struct OptArgs {
     int B, M, max_attempts;
@@ -67,8 +70,11 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // only when first attempts are finished, so speculation costs nothing; with few problems it halves the tail.
 // The warp whose completion resolves a problem assembles its outputs (final coefficients included).
 // MC: the number of pieces as a compile-time constant (loops over pieces/nodes unroll, lane maps fold).
-template <int MODE, int MC>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NEO_MIN_CTAS) k_optimize(const DevParams P, const OptArgs a)
+// MINB: CTAs per SM the register allocation is sized for. 2 (231 registers) is fastest when the launch is bound by the
+// longest chain of evaluations (few problems per SM); 3 (168 registers, 12 warps per SM) gives more throughput once
+// every SM has a queue of problems (launch_optimize picks by batch size; the arithmetic is the same).
+template <int MODE, int MC, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -292,6 +298,8 @@ struct MapSlot {
     Cell *cells = nullptr;
     int8_t *occ = nullptr;       // binarised grid of the last occupancy / point-cloud build
     size_t occ_cap = 0;
+    unsigned char *blocked = nullptr;   // has_collision over the enlarged A* grid (astar_warp.cuh), rebuilt with the map
+    size_t blocked_cap = 0;
     int H = 0, W = 0;
     double res = 0, ox = 0, oy = 0;
 };
@@ -318,6 +326,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    int min_ctas = 0;                // development switch (env NEO_MIN_CTAS_FORCE = 2 | 3): overrides the choice by batch size
     int lockstep = 0;                // development switch (env NEO_LOCKSTEP at neo_create): CTA-level lockstep, see k_optimize
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     char name[128] = {0};
@@ -405,6 +414,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     neo_handle *h = new neo_handle();
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps);
     if (const char *e = getenv("NEO_LOCKSTEP")) h->lockstep = atoi(e) != 0;
+    if (const char *e = getenv("NEO_MIN_CTAS_FORCE")) h->min_ctas = atoi(e);
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
     bool good = cudaSetDevice(device) == cudaSuccess &&
@@ -427,7 +437,7 @@ extern "C" int neo_destroy(neo_handle *h)
     if (!h) return NEO_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (auto &s : h->slots) { if (s.cells) cudaFree(s.cells); if (s.occ) cudaFree(s.occ); }
+    for (auto &s : h->slots) { if (s.cells) cudaFree(s.cells); if (s.occ) cudaFree(s.occ); if (s.blocked) cudaFree(s.blocked); }
     for (auto &b : h->bufs) if (b.p) cudaFree(b.p);
     if (h->pinned.p) cudaFreeHost(h->pinned.p);
     if (h->astar.p) cudaFree(h->astar.p);
@@ -475,9 +485,23 @@ static int slot_prepare(neo_handle *h, int slot, int H, int W, double res, doubl
 
 static int slot_publish(neo_handle *h, int slot)
 {
-    const MapSlot &s = h->slots[slot];
+    MapSlot &s = h->slots[slot];
     MapView v;
     v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy; v.inv_res = 1.0 / s.res;
+    v.blocked = nullptr;
+    // node-blocked grid of the geometric initializer (AP:130-141), one byte per node of the enlarged grid
+    const size_t nodes = astar_grid_cells(s.H, s.W, s.res);
+    if (s.blocked_cap < nodes) {
+        if (s.blocked) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(s.blocked)); s.blocked = nullptr; s.blocked_cap = 0; }
+        CK(cudaMalloc(&s.blocked, nodes));
+        s.blocked_cap = nodes;
+    }
+    const int pad = (int)(10.0 / s.res);
+    dim3 grid((s.W + pad + 127) / 128, s.H + pad);
+    k_astar_blocked<<<grid, 128, 0, h->stream>>>(v, s.blocked);
+    h->launches++;
+    CK(cudaGetLastError());
+    v.blocked = s.blocked;
     CK(cudaMemcpyAsync(h->d_maps + slot, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return NEO_OK;
@@ -632,6 +656,7 @@ extern "C" int neo_query_map(neo_handle *h, int slot, int n, const double *xy, i
     CK(cudaMemcpyAsync(base + o_xy, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
     MapView v;
     v.cells = s.cells; v.H = s.H; v.W = s.W; v.res = s.res; v.ox = s.ox; v.oy = s.oy; v.inv_res = 1.0 / s.res;
+    v.blocked = s.blocked;
     k_query<<<(n + 127) / 128, 128, 0, h->stream>>>(v, n, (const double *)(base + o_xy), (int32_t *)(base + o_idx),
                                                     (double *)(base + o_dis), (double *)(base + o_grad));
     h->launches++;
@@ -678,18 +703,21 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     // kernel variant: sampling schedule (minco_warp.cuh) by trajectory length; the shipped configuration (M = 3) and
     // the dense-map configuration (M = 10) get instantiations with the piece count as a compile-time constant
     void (*kern)(const DevParams, const OptArgs) = nullptr;
+    const bool packed = h->min_ctas ? h->min_ctas >= 3 : (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;
+#define NEO_K(MODE, MC) (packed ? k_optimize<MODE, MC, 3> : k_optimize<MODE, MC, NEO_MIN_CTAS>)
     switch (a.M) {      // one instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
-        case 2: kern = k_optimize<SAMPLE_BY_PIECE, 2>; break;
-        case 3: kern = k_optimize<SAMPLE_BY_PIECE, 3>; break;
-        case 4: kern = k_optimize<SAMPLE_BY_PIECE, 4>; break;
-        case 5: kern = k_optimize<SAMPLE_ALL_PIECES, 5>; break;
-        case 6: kern = k_optimize<SAMPLE_ALL_PIECES, 6>; break;
-        case 7: kern = k_optimize<SAMPLE_ALL_PIECES, 7>; break;
-        case 8: kern = k_optimize<SAMPLE_ALL_PIECES, 8>; break;
-        case 9: kern = k_optimize<SAMPLE_ALL_PIECES, 9>; break;
-        case 10: kern = k_optimize<SAMPLE_ALL_PIECES, 10>; break;
+        case 2: kern = NEO_K(SAMPLE_BY_PIECE, 2); break;
+        case 3: kern = NEO_K(SAMPLE_BY_PIECE, 3); break;
+        case 4: kern = NEO_K(SAMPLE_BY_PIECE, 4); break;
+        case 5: kern = NEO_K(SAMPLE_ALL_PIECES, 5); break;
+        case 6: kern = NEO_K(SAMPLE_ALL_PIECES, 6); break;
+        case 7: kern = NEO_K(SAMPLE_ALL_PIECES, 7); break;
+        case 8: kern = NEO_K(SAMPLE_ALL_PIECES, 8); break;
+        case 9: kern = NEO_K(SAMPLE_ALL_PIECES, 9); break;
+        case 10: kern = NEO_K(SAMPLE_ALL_PIECES, 10); break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
+#undef NEO_K
     int rc = prep_kernel(h, kern, a.M, &occ);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
@@ -1068,18 +1096,21 @@ static int astar_launch(neo_handle *h, int B, const double *start, const double 
     for (auto &s : h->slots)
         if (s.cells) { const size_t c = astar_grid_cells(s.H, s.W, s.res); cap = c > cap ? c : cap; }
     if (cap == 0) return fail(h, "neo_astar: no map uploaded");
-    if (cap > (size_t)0x7fffffff) return fail(h, "neo_astar: search grid too large for 32-bit cell indices");
-    const size_t per_warp = cap * (sizeof(AstarNode) + 2 * sizeof(int));
+    for (auto &s : h->slots)
+        if (s.cells && (s.W + (int)(10.0 / s.res) > 0xffff || s.H + (int)(10.0 / s.res) > 0x7fff))
+            return fail(h, "neo_astar: search grid too large (node coordinates are packed into 16 bits)");
+    const size_t per_warp = cap * ASTAR_BYTES_PER_CELL;
     size_t warps = (size_t)h->sm_count * ASTAR_WARPS_PER_SM;
     if (warps > ASTAR_SCRATCH_BUDGET / per_warp) warps = ASTAR_SCRATCH_BUDGET / per_warp;
     if (warps > (size_t)B) warps = B;
     if (warps < 1) warps = 1;
-    warps = (warps + 3) / 4 * 4;                                // whole CTAs of 4 warps
+    warps = (warps + ASTAR_WARPS_PER_CTA - 1) / ASTAR_WARPS_PER_CTA * ASTAR_WARPS_PER_CTA;     // whole CTAs
     if (h->astar_cap != cap || (size_t)h->astar_warps < warps) {
         if (h->astar.p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(h->astar.p)); h->astar.p = nullptr; }
         h->astar_cap = 0; h->astar_warps = 0;
         CK(cudaMalloc(&h->astar.p, per_warp * warps));
-        CK(cudaMemsetAsync(h->astar.p, 0, sizeof(AstarNode) * cap * warps, st));
+        CK(cudaMemsetAsync((char *)h->astar.p + sizeof(OpenRec) * cap * warps, 0, sizeof(AstarNode) * cap * warps, st));   // nodes untouched
+        CK(cudaFuncSetAttribute(k_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASTAR_SMEM_BYTES));
         h->astar_cap = cap; h->astar_warps = (int)warps;
     }
     AstarArgs a;
@@ -1087,13 +1118,13 @@ static int astar_launch(neo_handle *h, int B, const double *start, const double 
     a.B = B; a.max_closed = max_closed; a.max_path = max_path;
     a.path = path; a.path_len = path_len; a.status = status; a.closed = closed; a.pruned = pruned;
     const size_t laid = (size_t)h->astar_warps;                 // the layout follows the allocation, not this launch
-    a.nodes = (AstarNode *)h->astar.p;
-    a.open = (int *)((char *)h->astar.p + sizeof(AstarNode) * cap * laid);
-    a.order = a.open + cap * laid;
+    a.spill = (OpenRec *)h->astar.p;                            // 24-B records first (8-byte aligned), then nodes, then ints
+    a.nodes = (AstarNode *)((char *)h->astar.p + sizeof(OpenRec) * cap * laid);
+    a.order = (int *)((char *)a.nodes + sizeof(AstarNode) * cap * laid);
     a.cap = cap;
     a.counter = h->d_counter + 16;
     CK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
-    k_astar<<<(unsigned)(warps / 4), 128, 0, st>>>(a);
+    k_astar<<<(unsigned)(warps / ASTAR_WARPS_PER_CTA), ASTAR_WARPS_PER_CTA * 32, ASTAR_SMEM_BYTES, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;

@@ -29,7 +29,7 @@ def sim():
     lib = ctypes.CDLL(SO)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
 
-    def run(gm, start, target, max_path=512, max_closed=0):
+    def run(gm, start, target, max_path=512, max_closed=0, open_fast=512):
         start = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 2)
         target = np.ascontiguousarray(target, dtype=np.float64).reshape(-1, 2)
         B = start.shape[0]
@@ -37,7 +37,7 @@ def sim():
         out = dict(path=np.zeros((B, max_path, 2)), path_len=np.zeros(B, np.int32), pruned=np.zeros((B, 4, 2)),
                    status=np.zeros(B, np.int32), closed=np.zeros(B, np.int32))
         rc = lib.sim_astar(gm.H, gm.W, ctypes.c_double(gm.res), ctypes.c_double(gm.ox), ctypes.c_double(gm.oy),
-                           esdf.ctypes.data_as(dp), B, start.ctypes.data_as(dp), target.ctypes.data_as(dp), max_closed, max_path,
+                           esdf.ctypes.data_as(dp), B, start.ctypes.data_as(dp), target.ctypes.data_as(dp), max_closed, max_path, open_fast,
                            out['path'].ctypes.data_as(dp), out['path_len'].ctypes.data_as(ip), out['pruned'].ctypes.data_as(dp),
                            out['status'].ctypes.data_as(ip), out['closed'].ctypes.data_as(ip))
         assert rc == 0, 'search scratch was not restored'
@@ -52,17 +52,18 @@ def test_kernel_source_on_host_matches_reference_paths(golden, sim):
         sel = np.nonzero((g['world_id'] == wid) & (g['dense'] == dn))[0]
         w = make_world(wid, dense=bool(dn))
         gm = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
-        out = sim(gm, g['head'][sel, 0], g['tail'][sel, 0])
-        assert np.all(out['status'] == 0) and np.array_equal(out['path_len'], g['path_len'][sel])
-        assert np.array_equal(out['pruned'], g['pruned'][sel])
-        for j, i in enumerate(sel):
-            assert np.array_equal(out['path'][j, :g['path_len'][i]], g['path'][off[i]:off[i + 1]]), (wid, i)
+        for open_fast in (512, 5):           # 5: nearly the whole open list lives in the spill area
+            out = sim(gm, g['head'][sel, 0], g['tail'][sel, 0], open_fast=open_fast)
+            assert np.all(out['status'] == 0) and np.array_equal(out['path_len'], g['path_len'][sel])
+            assert np.array_equal(out['pruned'], g['pruned'][sel])
+            for j, i in enumerate(sel):
+                assert np.array_equal(out['path'][j, :g['path_len'][i]], g['path'][off[i]:off[i + 1]]), (wid, i)
 
 
 def test_kernel_source_on_host_edge_cases(golden, sim):
     g = golden('geo_M3.npz')
     gm = minco_ref.GridMap(g['tiny_occ'], 12, 16, 1.0, 0.0, 0.0)
-    out = sim(gm, [[2.5, 2.5]], [[10.5, 6.5]])
+    out = sim(gm, [[2.5, 2.5]], [[10.5, 6.5]], open_fast=16)
     assert out['status'][0] == 1 and out['closed'][0] == int(g['lost_closed'])
     assert np.array_equal(out['path'][0, :1], g['lost_path']) and np.array_equal(out['pruned'][0], g['lost_pruned'])
     out = sim(gm, [[2.5, 2.5], [-20.0, 0.0], [2.5, 2.5]], [[2.6, 2.7], [3.0, 3.0], [10.5, 6.5]], max_closed=10)
