@@ -18,7 +18,8 @@
 //   block elimination / back substitution                           lanes 0,1 (one per dimension)
 //   Hermite coefficients, energy cost+gradient (EP:345-390)          lanes 0..2M-1 (piece, dimension)
 //   sampled feasibility + collision penalties (EP:392-466)           all lanes over samples, ESDF cells from L1/L2,
-//                                                                    16-value butterfly ("transposed") warp reduction
+//                                                                    per-lane partial sums added per (piece, slot) in
+//                                                                    lane order through shared memory (no shuffles)
 //   adjoint, grad_q, grad_T, grad_tau (EP:485-537)                   lanes (node, dimension) / lanes 0..M-1
 #pragma once
 #include <cuda_runtime.h>
@@ -88,15 +89,19 @@ struct WarpMem {
     double *asg;   // [32]     cached lane assignment: piece + 16 * width + 1024 * rank
 };
 
-__host__ __device__ inline int warp_mem_doubles(int M)
+// staging rows of the sample loop's partial sums: one block of 15 rows per piece when all pieces are parked before the
+// owners add them (by-piece schedule, latency-optimised), one block otherwise (see eval_fg)
+__host__ __device__ inline int red_doubles(int M, bool one_block) { return (M > 4 || one_block) ? 15 * 33 : 15 * 33 * M; }
+
+__host__ __device__ inline int warp_mem_doubles(int M, bool one_block = false)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + (M > 4 ? 15 * 33 : 15 * 33 * M) + 4 * M + M + 32;
+              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + red_doubles(M, one_block) + 4 * M + M + 32;
     return (tot + 1) & ~1;
 }
 
-__device__ inline WarpMem carve(double *base, int M)
+__device__ inline WarpMem carve(double *base, int M, bool one_block = false)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     WarpMem m;
@@ -121,7 +126,7 @@ __device__ inline WarpMem carve(double *base, int M)
     m.Y = base; base += HIST * n;
     m.rho = base; base += HIST;
     m.al = base; base += HIST;
-    m.red = base; base += M > 4 ? 15 * 33 : 15 * 33 * M;   // per-lane partial sums: one block (all-pieces schedule) or one per piece
+    m.red = base; base += red_doubles(M, one_block);       // per-lane partial sums: one block or one per piece
     m.lw = base; base += 2 * M;
     m.pc = base; base += 2 * M;
     m.nsprev = base; base += M;
@@ -141,46 +146,6 @@ __device__ __forceinline__ double warp_max(double v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
-}
-
-// Reduce 16 per-lane values over the warp with 16 (not 80) double shuffles: after the call lane l holds in v[0]
-// the warp-wide total of slot (l >> 1).
-__device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane)
-{
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            double send = up ? v[i] : v[i + 8];
-            double keep = up ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            double send = up ? v[i] : v[i + 4];
-            double keep = up ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            double send = up ? v[i] : v[i + 2];
-            double keep = up ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 4);
-        }
-    }
-    {
-        const bool up = lane & 2;
-        double send = up ? v[0] : v[1];
-        double keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
-    }
-    v[0] += __shfl_xor_sync(FULL, v[0], 1);
 }
 
 // Called when a warp starts on a new problem: head/tail states into shared memory, cached lane assignment dropped.
@@ -302,6 +267,8 @@ struct EvalOut {
 
 constexpr int SAMPLE_BY_PIECE = 0;   // M <= 4
 constexpr int SAMPLE_ALL_PIECES = 1; // M >= 5
+constexpr int SAMPLE_BY_PIECE_STAGED = 2;   // M <= 4, throughput variant: one staging block, reduced after every piece
+                                            // (4 KB instead of 4 M KB of shared memory per warp -> more L1 for the map)
 
 // Exact quotient (p - origin)/res (ESDF:61-62) for the rare sample whose reciprocal estimate lies within 1e-9 of an
 // integer; kept out of line so the fp64 division sequence does not sit in the hot loop's instruction stream.
@@ -461,9 +428,14 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     NEO_TICK(4);
     // ---- sampled penalties (EP:392-466) -----------------------------------------------------------------
     double costs2 = 0.0, costs3 = 0.0;
-    if (MODE == SAMPLE_BY_PIECE) {
+    if (MODE == SAMPLE_BY_PIECE || MODE == SAMPLE_BY_PIECE_STAGED) {
         // few pieces (M <= 4): one piece at a time, lanes over its samples; every lane parks its 15 partial sums of the
         // piece in shared memory (row = (piece, slot), padded to 33 so that the owners below read conflict-free).
+        // Owner (piece, slot) adds the 32 per-lane partial sums in lane order (four interleaved chains): uniform trip
+        // counts, no shuffles, deterministic. SAMPLE_BY_PIECE parks all pieces first and lets 15 M owners work at once
+        // (shortest dependent chain); SAMPLE_BY_PIECE_STAGED re-uses one block and reduces after every piece (same
+        // additions in the same order, a third of the shared memory).
+        constexpr bool STAGED = MODE == SAMPLE_BY_PIECE_STAGED;
 #pragma unroll 1
         for (int i = 0; i < M; i++) {            // not unrolled: ONE copy of the sample body in the instruction stream
             const int ns = (int)m.nsd[2 * i];                    // int(T/delta_t) (EP:401)
@@ -476,25 +448,39 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
 #pragma unroll
             for (int s2 = 0; s2 < 16; s2++) acc[s2] = 0.0;
             for (int j = lane; j < ns; j += 32) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
-            double *row = m.red + (15 * i) * 33 + lane;
+            double *row = m.red + (STAGED ? 0 : 15 * i) * 33 + lane;
 #pragma unroll
             for (int s2 = 0; s2 < 15; s2++) row[s2 * 33] = acc[s2];
-        }
-        __syncwarp();
-        // owner o = (piece, slot) adds the 32 per-lane partial sums in lane order (four interleaved chains): uniform
-        // trip counts, no shuffles, deterministic
-        for (int o = lane; o < 15 * M; o += 32) {
-            const double *p = m.red + o * 33;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (STAGED) {
+                __syncwarp();
+                if (lane < 15) {
+                    const double *p = m.red + lane * 33;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
-            const double tot = (a0 + a1) + (a2 + a3);
-            const int i = o / 15, s2 = o - 15 * i;
-            if (s2 < 12) m.gC[12 * i + s2] += tot;
-            else if (s2 == 12) m.gT[i] += tot;
-            else m.pc[2 * i + (s2 - 13)] = tot;
+                    for (int k = 0; k < 32; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
+                    const double tot = (a0 + a1) + (a2 + a3);
+                    if (lane < 12) m.gC[12 * i + lane] += tot;
+                    else if (lane == 12) m.gT[i] += tot;
+                    else m.pc[2 * i + (lane - 13)] = tot;
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
+        if (!STAGED) {
+            __syncwarp();
+            for (int o = lane; o < 15 * M; o += 32) {
+                const double *p = m.red + o * 33;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
+                const double tot = (a0 + a1) + (a2 + a3);
+                const int i = o / 15, s2 = o - 15 * i;
+                if (s2 < 12) m.gC[12 * i + s2] += tot;
+                else if (s2 == 12) m.gT[i] += tot;
+                else m.pc[2 * i + (s2 - 13)] = tot;
+            }
+            __syncwarp();
+        }
         for (int i = 0; i < M; i++) { costs2 += m.pc[2 * i]; costs3 += m.pc[2 * i + 1]; }
     } else {
         // many pieces: the 32 lanes are split among the pieces in proportion to their sample counts (every piece with

@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int M = MC > 0 ? MC : a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M, A = a.max_attempts;
-    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
+    constexpr bool ONE_BLOCK = MODE == SAMPLE_BY_PIECE_STAGED;
+    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M, ONE_BLOCK), M, ONE_BLOCK);
     const unsigned total = (unsigned)A * (unsigned)a.B;
     for (;;) {
         unsigned int tid = 0;
@@ -326,6 +327,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    int staged = -1;                 // development switch (env NEO_STAGED = 0 | 1; default -1: by shared-memory fit)
     int min_ctas = 0;                // development switch (env NEO_MIN_CTAS_FORCE = 2 | 3): overrides the choice by batch size
     int lockstep = 0;                // development switch (env NEO_LOCKSTEP at neo_create): CTA-level lockstep, see k_optimize
     int sm_count = 0, cc_major = 0, cc_minor = 0;
@@ -415,6 +417,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps);
     if (const char *e = getenv("NEO_LOCKSTEP")) h->lockstep = atoi(e) != 0;
     if (const char *e = getenv("NEO_MIN_CTAS_FORCE")) h->min_ctas = atoi(e);
+    if (const char *e = getenv("NEO_STAGED")) h->staged = atoi(e) != 0 ? 1 : 0;
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
     bool good = cudaSetDevice(device) == cudaSuccess &&
@@ -683,12 +686,15 @@ static int check_problem(neo_handle *h, int B, int M)
     return NEO_OK;
 }
 
-static size_t smem_bytes(int M) { return sizeof(double) * (size_t)warp_mem_doubles(M) * WARPS_PER_CTA; }
+static size_t smem_bytes(int M, bool one_block = false)
+{
+    return sizeof(double) * (size_t)warp_mem_doubles(M, one_block) * WARPS_PER_CTA;
+}
 
 template <typename K>
-static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm)
+static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm, bool one_block = false)
 {
-    const size_t smem = smem_bytes(M);
+    const size_t smem = smem_bytes(M, one_block);
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, WARPS_PER_CTA * 32, smem));
@@ -704,11 +710,15 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     // the dense-map configuration (M = 10) get instantiations with the piece count as a compile-time constant
     void (*kern)(const DevParams, const OptArgs) = nullptr;
     const bool packed = h->min_ctas ? h->min_ctas >= 3 : (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;
+    // staged sums only where parking all pieces would cost the third CTA its shared memory (M = 4: 3 x 80 KB > 227 KB;
+    // measured +21 % there, +1 % at M = 3, -4 % at M = 2: scripts/gpu_ab_min_ctas.py staged)
+    const bool staged = packed && a.M <= 4 && (h->staged > 0 || (h->staged < 0 && 3 * (smem_bytes(a.M) + 1024) > (size_t)227 * 1024));
 #define NEO_K(MODE, MC) (packed ? k_optimize<MODE, MC, 3> : k_optimize<MODE, MC, NEO_MIN_CTAS>)
+#define NEO_KP(MC) (staged ? k_optimize<SAMPLE_BY_PIECE_STAGED, MC, 3> : NEO_K(SAMPLE_BY_PIECE, MC))
     switch (a.M) {      // one instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
-        case 2: kern = NEO_K(SAMPLE_BY_PIECE, 2); break;
-        case 3: kern = NEO_K(SAMPLE_BY_PIECE, 3); break;
-        case 4: kern = NEO_K(SAMPLE_BY_PIECE, 4); break;
+        case 2: kern = NEO_KP(2); break;
+        case 3: kern = NEO_KP(3); break;
+        case 4: kern = NEO_KP(4); break;
         case 5: kern = NEO_K(SAMPLE_ALL_PIECES, 5); break;
         case 6: kern = NEO_K(SAMPLE_ALL_PIECES, 6); break;
         case 7: kern = NEO_K(SAMPLE_ALL_PIECES, 7); break;
@@ -718,7 +728,8 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
 #undef NEO_K
-    int rc = prep_kernel(h, kern, a.M, &occ);
+#undef NEO_KP
+    int rc = prep_kernel(h, kern, a.M, &occ, staged);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
     const size_t need = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -736,7 +747,7 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.lockstep = h->lockstep;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
-    kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M, staged), st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;

@@ -197,3 +197,18 @@ def test_map_cache_reuploads_a_new_map_object():
     m = NS(occ=np.zeros((4, 4), np.int8), H=4, W=4, res=1.0, ox=0.0, oy=0.0)
     cache.ensure(0, m); cache.ensure(0, m)
     assert len(fh.uploads) == 7
+
+
+def test_four_key_indices_follow_the_reference_rule():
+    """geo.four_key_indices (GEO:78-95) against the checker's statement of the same rule on random key lists."""
+    from neo_planner_b200.geo import four_key_indices, geo_times
+    from oracle import astar_ref
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 4, 5, 6, 9, 17):
+        for _ in range(40):
+            keys = [0] if n == 1 else [0] + sorted(rng.choice(np.arange(1, 400), size=n - 1, replace=False).tolist())
+            got = four_key_indices(keys)
+            assert got == astar_ref.four_of(keys) and len(got) == 4 and got[0] == 0 and got[-1] == keys[-1]
+            assert all(isinstance(v, int) for v in got)
+    ts = geo_times(YamlConfig())
+    assert ts.tolist() == [3.75, 2.5, 3.75] and geo_times(YamlConfig(), 5).shape == (5, 3)
