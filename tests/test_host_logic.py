@@ -212,3 +212,25 @@ def test_four_key_indices_follow_the_reference_rule():
             assert all(isinstance(v, int) for v in got)
     ts = geo_times(YamlConfig())
     assert ts.tolist() == [3.75, 2.5, 3.75] and geo_times(YamlConfig(), 5).shape == (5, 3)
+
+
+def test_T2tau_host_matches_python_math_with_repeats():
+    """neo_T2tau (host libm log behind a small per-call memo) against the reference's formula (EP:468-475) evaluated with
+    Python's math.log: bit-identical for repeated, distinct and invalid durations in one call."""
+    import ctypes as C
+    import math
+    cfg = lib.Config.from_config(YamlConfig())
+    rng = np.random.default_rng(3)
+    base = np.array([3.75, 2.5, 3.75, 0.5, 5.0, 0.4, 5.5, 0.5000001, 4.9999999])
+    ts = np.concatenate([base, rng.uniform(0.5, 5.0, 5000), np.tile(base, 40), rng.choice(rng.uniform(0.6, 4.9, 37), 3000)])
+    tau = np.zeros_like(ts); st = np.zeros(ts.size, np.int32)
+    assert lib.load().neo_T2tau(C.byref(cfg), ts.size, lib.ptr(ts), lib.ptr(tau), lib.ptr(st)) == 0
+    for T, t, s in zip(ts, tau, st):
+        try:
+            want = -math.log((5.0 - 0.5) / (float(T) - 0.5) - 1)      # Python floats: T == T_min divides by zero
+            assert s == 0 and t == want, (T, t, want)
+        except (ValueError, ZeroDivisionError):
+            assert s == lib.ST_DOMAIN and t == 0.0, (T, s)
+    bad = np.array([np.nan, 2.5]); tau = np.zeros(2); st = np.zeros(2, np.int32)      # NaN durations are rejected up front
+    lib.load().neo_T2tau(C.byref(cfg), 2, lib.ptr(bad), lib.ptr(tau), lib.ptr(st))
+    assert st.tolist() == [lib.ST_DOMAIN, 0]
