@@ -53,6 +53,7 @@ def lib():
         _lib = C.CDLL(build())
         _lib.orc_get_coeffs.restype = C.c_int
         _lib.orc_sample_count.restype = C.c_int
+        _lib.orc_set_trace.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_sample_count.argtypes = [C.c_int, C.c_void_p, C.c_double]
         _lib.orc_sample.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         _lib.orc_esdf_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -632,6 +632,14 @@ typedef struct {
     int status, nit, nfev;
 } orc_result;
 
+/* Optional trace for offline analysis of the evaluation chain (scripts/analyze_chain.py): one int per line search,
+ * evals * 4 + failed * 2 + (memory non-empty at its start), preceded by -1 for every minimize() call. */
+static int *orc_trace_buf = 0;
+static int orc_trace_cap = 0, orc_trace_len = 0;
+void orc_set_trace(int *buf, int cap) { orc_trace_buf = buf; orc_trace_cap = cap; orc_trace_len = 0; }
+int orc_trace_count(void) { return orc_trace_len; }
+static void orc_trace_put(int v) { if (orc_trace_buf && orc_trace_len < orc_trace_cap) orc_trace_buf[orc_trace_len++] = v; }
+
 /* plan_once's minimize() call. tol=1e-4 -> ftol = gtol = 1e-4; maxcor 10; maxls 20; maxiter = maxfun = 15000. */
 int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
                const double *x0, orc_result *out)
@@ -649,6 +657,7 @@ int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *hea
     f = costs[0] * p->w[0] + costs[1] * p->w[1] + costs[2] * p->w[2] + costs[3] * p->w[3];
     nfev = 1; memcpy(xl, x, sizeof(double) * n);
     memcpy(out->costs, costs, sizeof(costs));
+    orc_trace_put(-1);
     double sbg = 0.0; for (int i = 0; i < n; i++) sbg = fmax(sbg, fabs(g[i]));
     if (sbg <= pgtol) { st = ORC_CONV_PG; goto done; }
     for (;;) {
@@ -672,6 +681,7 @@ int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *hea
         memcpy(t, x, sizeof(double) * n); memcpy(r, g, sizeof(double) * n); fold = f;
         double gd = dotn(n, g, d), gdold = gd;
         int fail = 0;
+        const int nfev_ls = nfev;
         if (gd >= 0.0) fail = 1;
         else {
             dcs_state ls; dcsrch_start(&ls, stp, f, gd);
@@ -695,6 +705,7 @@ int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *hea
                 if (task) break;
             }
         }
+        orc_trace_put((nfev - nfev_ls) * 4 + fail * 2 + (col > 0));
         if (fail) {
             memcpy(x, t, sizeof(double) * n); memcpy(g, r, sizeof(double) * n); f = fold;
             if (col == 0) { st = ORC_ABNORMAL; goto done; }
