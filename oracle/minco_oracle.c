@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #include <float.h>
 
 #define ORC_D 2
@@ -640,24 +641,33 @@ void orc_set_trace(int *buf, int cap) { orc_trace_buf = buf; orc_trace_cap = cap
 int orc_trace_count(void) { return orc_trace_len; }
 static void orc_trace_put(int v) { if (orc_trace_buf && orc_trace_len < orc_trace_cap) orc_trace_buf[orc_trace_len++] = v; }
 
-/* plan_once's minimize() call. tol=1e-4 -> ftol = gtol = 1e-4; maxcor 10; maxls 20; maxiter = maxfun = 15000. */
-int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
-               const double *x0, orc_result *out)
+/* Restart states for the analysis of speculative restarts: what the optimizer would continue
+ * from if the line search that is about to start failed -- captured at the start of every line search that has memory. */
+typedef struct {
+    double x[ORC_MAXN], g[ORC_MAXN], f, costs[4];
+    int nit, nfev;          /* counters at the start of the line search */
+    int failed, nfev_after; /* set when that line search failed: evaluations counted up to the failure */
+} orc_restart;
+static orc_restart *orc_snap_buf = 0;
+static int orc_snap_cap = 0, orc_snap_len = 0;
+void orc_set_snapshots(orc_restart *buf, int cap) { orc_snap_buf = buf; orc_snap_cap = cap; orc_snap_len = 0; }
+int orc_snapshot_count(void) { return orc_snap_len; }
+
+/* The L-BFGS-B iteration from a given iterate (x, f, g known, memory empty). plan_once's minimize() call:
+ * tol=1e-4 -> ftol = gtol = 1e-4; maxcor 10; maxls 20; maxiter = maxfun = 15000. have_xl: x is the last evaluated point. */
+static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
+                       const double *x_in, const double *g_in, double f, int nit, int nfev, int have_xl, orc_result *out)
 {
     const int n = ORC_D * (M - 1) + M, m = ORC_HIST, maxls = 20, maxiter = 15000, maxfun = 15000;
     const double pgtol = 1e-4, ftol = 1e-4, epsmch = DBL_EPSILON;
     const double tol = (ftol / epsmch) * epsmch;
     double x[ORC_MAXN], g[ORC_MAXN], d[ORC_MAXN], t[ORC_MAXN], r[ORC_MAXN], xl[ORC_MAXN], xn[ORC_MAXN];
     double S[ORC_HIST][ORC_MAXN], Y[ORC_HIST][ORC_MAXN], rho[ORC_HIST], al[ORC_HIST];
-    double costs[4], f, fold, theta = 1.0;
-    int col = 0, head_i = 0, nit = 0, nfev = 0, st;
-    memcpy(x, x0, sizeof(double) * n);
-    st = orc_eval(p, map, M, head, tail, x, costs, g, 0, 0);
-    if (st) { out->status = st; out->nit = 0; out->nfev = 0; memcpy(out->x, x, sizeof(double) * n); return st; }
-    f = costs[0] * p->w[0] + costs[1] * p->w[1] + costs[2] * p->w[2] + costs[3] * p->w[3];
-    nfev = 1; memcpy(xl, x, sizeof(double) * n);
-    memcpy(out->costs, costs, sizeof(costs));
-    orc_trace_put(-1);
+    double costs[4], fold, theta = 1.0;
+    int col = 0, head_i = 0, st;
+    memcpy(x, x_in, sizeof(double) * n); memcpy(g, g_in, sizeof(double) * n);
+    if (have_xl) memcpy(xl, x, sizeof(double) * n);
+    else for (int i = 0; i < n; i++) xl[i] = NAN;      /* a speculative restart does not know the failed search's last trial */
     double sbg = 0.0; for (int i = 0; i < n; i++) sbg = fmax(sbg, fabs(g[i]));
     if (sbg <= pgtol) { st = ORC_CONV_PG; goto done; }
     for (;;) {
@@ -680,8 +690,14 @@ int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *hea
         double stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
         memcpy(t, x, sizeof(double) * n); memcpy(r, g, sizeof(double) * n); fold = f;
         double gd = dotn(n, g, d), gdold = gd;
-        int fail = 0;
+        int fail = 0, snap = -1;
         const int nfev_ls = nfev;
+        if (col > 0 && orc_snap_buf && orc_snap_len < orc_snap_cap) {
+            orc_restart *rs = &orc_snap_buf[snap = orc_snap_len++];
+            memcpy(rs->x, x, sizeof(double) * n); memcpy(rs->g, g, sizeof(double) * n);
+            rs->f = f; memcpy(rs->costs, out->costs, sizeof(rs->costs));
+            rs->nit = nit; rs->nfev = nfev; rs->failed = 0; rs->nfev_after = 0;
+        }
         if (gd >= 0.0) fail = 1;
         else {
             dcs_state ls; dcsrch_start(&ls, stp, f, gd);
@@ -706,6 +722,7 @@ int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *hea
             }
         }
         orc_trace_put((nfev - nfev_ls) * 4 + fail * 2 + (col > 0));
+        if (fail && snap >= 0) { orc_snap_buf[snap].failed = 1; orc_snap_buf[snap].nfev_after = nfev; }
         if (fail) {
             memcpy(x, t, sizeof(double) * n); memcpy(g, r, sizeof(double) * n); f = fold;
             if (col == 0) { st = ORC_ABNORMAL; goto done; }
@@ -735,6 +752,60 @@ done:
     memcpy(out->x, x, sizeof(double) * n);
     out->f = f; out->status = st; out->nit = nit; out->nfev = nfev;
     return st;
+}
+
+int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
+               const double *x0, orc_result *out)
+{
+    const int n = ORC_D * (M - 1) + M;
+    double g[ORC_MAXN], costs[4];
+    int st = orc_eval(p, map, M, head, tail, x0, costs, g, 0, 0);
+    if (st) { out->status = st; out->nit = 0; out->nfev = 0; memcpy(out->x, x0, sizeof(double) * n); return st; }
+    const double f = costs[0] * p->w[0] + costs[1] * p->w[1] + costs[2] * p->w[2] + costs[3] * p->w[3];
+    memcpy(out->costs, costs, sizeof(costs));
+    orc_trace_put(-1);
+    return lbfgsb_core(p, map, M, head, tail, x0, g, f, 0, 1, 1, out);
+}
+
+/* Continue from a captured restart state as a speculative restart would: memory empty, first step 1, no evaluation at
+ * the start point; the evaluation counter resumes from the count at the failure. */
+int orc_lbfgsb_resume(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
+                      const orc_restart *rs, orc_result *out)
+{
+    memcpy(out->costs, rs->costs, sizeof(rs->costs));
+    return lbfgsb_core(p, map, M, head, tail, rs->x, rs->g, rs->f, rs->nit, rs->nfev_after, 0, out);
+}
+
+/* Design check for speculative restarts: run minimize() from x0, then replay every line search that failed with a
+ * non-empty memory from its captured restart state. Returns how many replays do NOT end in the original result
+ * (status, nit, nfev, x and last-evaluated costs bit for bit); *checked = number of replays. */
+int orc_check_restarts(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
+                       const double *x0, int *checked)
+{
+    static orc_restart snaps[2048];
+    const int n = ORC_D * (M - 1) + M;
+    orc_result ref, r;
+    orc_set_snapshots(snaps, 2048);
+    orc_lbfgsb(p, map, M, head, tail, x0, &ref);
+    const int ns = orc_snapshot_count();
+    orc_set_snapshots(0, 0);
+    int bad = 0;
+    *checked = 0;
+    for (int i = 0; i < ns; i++) {
+        if (!snaps[i].failed) continue;
+        orc_lbfgsb_resume(p, map, M, head, tail, &snaps[i], &r);
+        (*checked)++;
+        /* costs only matter when minimize() returns: an exception (status >= ORC_OVERFLOW) discards the attempt (EP:197) */
+        if (r.status != ref.status || r.nit != ref.nit || r.nfev != ref.nfev || memcmp(r.x, ref.x, sizeof(double) * n) ||
+            (ref.status < ORC_OVERFLOW && memcmp(r.costs, ref.costs, sizeof(ref.costs)))) {
+            bad++;
+            if (getenv("ORC_DEBUG_RESTARTS"))
+                fprintf(stderr, "snap %d/%d: status %d/%d nit %d/%d nfev %d/%d xdiff %d costdiff %d (snap nit %d nfev %d after %d)\n", i, ns,
+                        r.status, ref.status, r.nit, ref.nit, r.nfev, ref.nfev, memcmp(r.x, ref.x, sizeof(double) * n) != 0,
+                        memcmp(r.costs, ref.costs, sizeof(ref.costs)) != 0, snaps[i].nit, snaps[i].nfev, snaps[i].nfev_after);
+        }
+    }
+    return bad;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -270,3 +270,30 @@ def test_astar_oracle_unreachable_target(golden):
     assert not found and np.array_equal(np.array(path), g['lost_path']) and nclosed == int(g['lost_closed'])
     assert np.array_equal(np.array(astar_ref.prune(gm, path)[0]), g['lost_pruned'])
     assert astar_ref.astar_plain(gm, [2.5, 2.5], [10.5, 6.5]) == path
+
+
+def test_restart_state_reproduces_the_continuation_after_a_failed_line_search():
+    """Design pin for speculative restarts: {x, g, f, nit, nfev at the failure} captured at the start of
+    a line search is all the optimizer needs to continue after that search fails -- replaying from it (empty memory,
+    first step 1, no evaluation at the start point) ends in the same status, counters, x and costs."""
+    import ctypes as C
+    from neo_planner_b200 import guesses
+    from neo_planner_b200.worlds import make_problems, make_world, YamlConfig
+    from oracle import c_oracle
+    cfg = YamlConfig(); M = 3
+    w = make_world(0)
+    head, tail = make_problems(w, 96, M=M)
+    q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
+    p = c_oracle.Params.from_config(cfg); m = c_oracle.OracleMap.from_world(w)
+    hp, tp = c_oracle.pad_state(head), c_oracle.pad_state(tail)
+    lib = c_oracle.lib()
+    replayed = 0
+    for b in range(96):
+        tau = -np.log((cfg.T_max - cfg.T_min) / (ts0[b] - cfg.T_min) - 1)
+        x0 = np.ascontiguousarray(np.concatenate((q0[b].reshape(-1), tau)))
+        chk = C.c_int(0)
+        bad = lib.orc_check_restarts(C.byref(p), C.byref(m.c), C.c_int(M), hp[b].ctypes.data_as(C.c_void_p),
+                                     tp[b].ctypes.data_as(C.c_void_p), x0.ctypes.data_as(C.c_void_p), C.byref(chk))
+        assert bad == 0, b
+        replayed += chk.value
+    assert replayed >= 20
