@@ -1111,6 +1111,7 @@ static int astar_launch(neo_handle *h, int B, const double *start, const double 
         if (s.cells && (s.W + (int)(10.0 / s.res) > 0xffff || s.H + (int)(10.0 / s.res) > 0x7fff))
             return fail(h, "neo_astar: search grid too large (node coordinates are packed into 16 bits)");
     const size_t per_warp = cap * ASTAR_BYTES_PER_CELL;
+    if (per_warp > ASTAR_SCRATCH_BUDGET) return fail(h, "neo_astar: search grid too large for the per-warp scratch budget");
     size_t warps = (size_t)h->sm_count * ASTAR_WARPS_PER_SM;
     if (warps > ASTAR_SCRATCH_BUDGET / per_warp) warps = ASTAR_SCRATCH_BUDGET / per_warp;
     if (warps > (size_t)B) warps = B;
