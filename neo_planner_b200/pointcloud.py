@@ -4,7 +4,7 @@
 goes straight to the device: k_points_to_occ -> exact EDT -> gradient (csrc/map_kernels.cuh).
 
 Projection semantics are restated from the launch parameters only (octomap_server is not in the reference repo):
-parity of this step is pinned to a NumPy statement of the same rule and to the survey's cell count for
+parity of this step is pinned to a NumPy statement of the same rule (oracle/pointcloud_ref.py) and to the survey's cell count for
 `src/simulator/worlds/poles.pcd`, not to octomap_server itself."""
 from __future__ import annotations
 
@@ -37,14 +37,3 @@ def grid_for(points, res, margin=0.0):
     W = int(np.floor((hi[0] - lo[0]) / res)) + 1
     H = int(np.floor((hi[1] - lo[1]) / res)) + 1
     return float(lo[0]), float(lo[1]), H, W
-
-
-def project_numpy(points, z_min, z_max, H, W, res, ox, oy):
-    """NumPy statement of the projection rule (test oracle for k_points_to_occ)."""
-    p = np.asarray(points, dtype=np.float32).astype(np.float64)
-    m = (p[:, 2] >= z_min) & (p[:, 2] <= z_max)
-    c = np.floor((p[m, 0] - ox) / res); r = np.floor((p[m, 1] - oy) / res)
-    ok = (r >= 0) & (r < H) & (c >= 0) & (c < W)
-    occ = np.zeros((H, W), np.int8)
-    occ[r[ok].astype(int), c[ok].astype(int)] = 100
-    return occ

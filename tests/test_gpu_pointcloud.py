@@ -8,7 +8,7 @@ import pytest
 
 from neo_planner_b200 import lib, pointcloud
 from neo_planner_b200.worlds import YamlConfig
-from oracle import c_oracle
+from oracle import c_oracle, pointcloud_ref
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -38,7 +38,7 @@ def test_poles_pointcloud_to_esdf():
     h.set_map_points(0, pts, z_min, z_max, H, W, res, ox, oy)
     occ = h.get_occupancy(0, H, W)
     assert int((occ == 100).sum()) == 1454                      # SURVEY.md §8c probe of the same file
-    assert np.array_equal(occ, pointcloud.project_numpy(pts, z_min, z_max, H, W, res, ox, oy))
+    assert np.array_equal(occ, pointcloud_ref.project_numpy(pts, z_min, z_max, H, W, res, ox, oy))
     e, gx, gy = h.get_map(0, H, W)
     m = c_oracle.OracleMap(occ, H, W, res, ox, oy)              # checker pinned bit-exact to scipy/numpy
     assert np.array_equal(e, m.esdf) and np.array_equal(gx, m.gx) and np.array_equal(gy, m.gy)
