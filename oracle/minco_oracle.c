@@ -653,6 +653,18 @@ static int orc_snap_cap = 0, orc_snap_len = 0;
 void orc_set_snapshots(orc_restart *buf, int cap) { orc_snap_buf = buf; orc_snap_cap = cap; orc_snap_len = 0; }
 int orc_snapshot_count(void) { return orc_snap_len; }
 
+/* Hooks for the protocol simulator of speculative restarts (oracle/shadow_sim.c); NULL everywhere else. */
+typedef struct {
+    void *ctx;
+    /* a line search with non-empty memory is about to start from (x, g, f); counters at that moment */
+    void (*ls_start)(void *ctx, int n, const double *x, const double *g, double f, const double *costs, int nit, int nfev);
+    void (*ls_end)(void *ctx);                  /* that search ended without failing (accepted point or exception) */
+    int (*ls_fail)(void *ctx, int nfev, const double *costs);   /* it failed; 1 = a shadow took the task over: retire */
+    int (*poll)(void *ctx);                     /* before every evaluation; 1 = stop (cancelled / superseded) */
+} orc_hooks;
+static __thread const orc_hooks *orc_hooks_cur = 0;
+enum { ORC_STOPPED = 8, ORC_HANDED_OFF = 9 };
+
 /* The L-BFGS-B iteration from a given iterate (x, f, g known, memory empty). plan_once's minimize() call:
  * tol=1e-4 -> ftol = gtol = 1e-4; maxcor 10; maxls 20; maxiter = maxfun = 15000. have_xl: x is the last evaluated point. */
 static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
@@ -692,6 +704,9 @@ static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const dou
         double gd = dotn(n, g, d), gdold = gd;
         int fail = 0, snap = -1;
         const int nfev_ls = nfev;
+        const orc_hooks *hk = orc_hooks_cur;
+        const int published = hk && col > 0;
+        if (published) hk->ls_start(hk->ctx, n, x, g, f, out->costs, nit, nfev);
         if (col > 0 && orc_snap_buf && orc_snap_len < orc_snap_cap) {
             orc_restart *rs = &orc_snap_buf[snap = orc_snap_len++];
             memcpy(rs->x, x, sizeof(double) * n); memcpy(rs->g, g, sizeof(double) * n);
@@ -710,7 +725,9 @@ static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const dou
                 int same = 1; for (int i = 0; i < n; i++) if (xn[i] != xl[i]) { same = 0; break; }
                 memcpy(x, xn, sizeof(double) * n);
                 if (!same) {   /* scipy's ScalarFunction does not re-evaluate an unchanged x */
+                    if (hk && hk->poll(hk->ctx)) { out->status = ORC_STOPPED; out->nit = nit; out->nfev = nfev; return ORC_STOPPED; }
                     st = orc_eval(p, map, M, head, tail, x, costs, g, 0, 0);
+                    if (st && published) hk->ls_end(hk->ctx);
                     if (st) { out->status = st; out->nit = nit; out->nfev = nfev; memcpy(out->x, x, sizeof(double) * n); return st; }
                     f = costs[0] * p->w[0] + costs[1] * p->w[1] + costs[2] * p->w[2] + costs[3] * p->w[3];
                     nfev++; memcpy(xl, x, sizeof(double) * n);
@@ -723,6 +740,11 @@ static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const dou
         }
         orc_trace_put((nfev - nfev_ls) * 4 + fail * 2 + (col > 0));
         if (fail && snap >= 0) { orc_snap_buf[snap].failed = 1; orc_snap_buf[snap].nfev_after = nfev; }
+        if (published && !fail) hk->ls_end(hk->ctx);
+        if (published && fail && hk->ls_fail(hk->ctx, nfev, out->costs)) {
+            out->status = ORC_HANDED_OFF; out->nit = nit; out->nfev = nfev;
+            return ORC_HANDED_OFF;
+        }
         if (fail) {
             memcpy(x, t, sizeof(double) * n); memcpy(g, r, sizeof(double) * n); f = fold;
             if (col == 0) { st = ORC_ABNORMAL; goto done; }
