@@ -147,10 +147,44 @@ struct OptOut {
 // cancel_word/cancel_mask: when (*cancel_word & cancel_mask) becomes non-zero (an earlier attempt of the same problem
 // has been accepted, so this speculative attempt can never be the returned one) the run stops with ST_CANCELLED.
 constexpr int ST_CANCELLED = 7;
-template <int MODE>
+
+// ---- speculative restarts (EXPERIMENTAL, off by default: NEO_SHADOW=1; protocol = oracle/shadow_sim.c) --------------
+// The owner of a task publishes, at the start of every line search that has memory, the state the optimizer would
+// restart from if that search failed. A warp with nothing else to do claims the request and computes the restart
+// speculatively; a successful search cancels it (epoch change), a failed one hands the task over to it.
+constexpr int ST_SUPERSEDED = 8;     // a speculative restart that was not needed (never reported)
+constexpr int ST_HANDED_OFF = 9;     // the owner retired in favour of its claimant (never reported)
+enum { SL_IDLE = 0, SL_REQUESTED = 1, SL_CLAIMED = 2, SL_CONFIRMED = 3 };
+__device__ __forceinline__ unsigned sl_ctl(unsigned epoch, unsigned state) { return epoch * 4u + state; }
+
+struct ShadowSlot {                  // one per task (attempt * B + problem), zero-initialised per launch
+    unsigned ctl;                    // epoch * 4 + state
+    int nit, nfev, nfev_after;       // counters at the start of the search / at its failure (hand-off)
+    unsigned long long ns, nv, nc, nanos;                          // work counters at the start of the search
+    unsigned long long ns_after, nv_after, nc_after, nanos_after;  // ... at the failure
+    double f;
+    double costs[4];
+    double x[32], g[32];
+};
+
+struct ShadowCtx {                   // warp-uniform
+    ShadowSlot *slot;
+    unsigned epoch;                  // owner: last published epoch; claimant: the epoch it claimed
+    bool owner;                      // true: owns the task and publishes; false: speculative
+    bool published;                  // owner: the running line search has a request out
+    unsigned long long t_start;      // %globaltimer when this warp started on the task
+    unsigned long long nanos_base;   // time earlier owners spent on the task
+};
+
+__device__ __forceinline__ unsigned sl_load(const ShadowSlot *slot)
+{
+    return *reinterpret_cast<const volatile unsigned *>(&slot->ctl);
+}
+
+template <int MODE, bool SHADOW = false>
 __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
                                    double x0l, OptOut &o, const unsigned *cancel_word = nullptr,
-                                   unsigned cancel_mask = 0u, bool lockstep = false)
+                                   unsigned cancel_mask = 0u, bool lockstep = false, ShadowCtx *sc = nullptr)
 {
     const int n = 3 * M - 2;
     const bool mine = lane < n;
@@ -163,23 +197,60 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
     bool first = true;
     Dcsrch ls;
     o.ns = o.nv = o.nc = 0;
+    bool resume = false;
+    if constexpr (SHADOW) {
+        if (!sc->owner) {
+            // claimant: continue from the published restart state (memory empty, no evaluation at the start point)
+            const ShadowSlot *sl = sc->slot;
+            x = mine ? __ldcg(&sl->x[lane]) : 0.0; g = mine ? __ldcg(&sl->g[lane]) : 0.0;
+            f = __ldcg(&sl->f); nit = __ldcg(&sl->nit); nfev = __ldcg(&sl->nfev);
+            o.ns = __ldcg(&sl->ns); o.nv = __ldcg(&sl->nv); o.nc = __ldcg(&sl->nc);
+            sc->nanos_base = __ldcg(&sl->nanos);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o.costs[k] = __ldcg(&sl->costs[k]);
+            __threadfence();
+            const unsigned c = sl_load(sl);           // seqlock: the copy counts only if the owner has not moved on
+            if (c != sl_ctl(sc->epoch, SL_CLAIMED) && c != sl_ctl(sc->epoch, SL_CONFIRMED)) { o.status = ST_SUPERSEDED; return; }
+            xlast = __longlong_as_double(0x7ff8000000000000LL);       // the failed search's last trial point is unknown
+            first = false; resume = true;
+        }
+    }
     for (;;) {
         // Large batches: the warps of a CTA meet here before every evaluation so that they walk through the (~60 KB)
         // evaluator together and share its instruction fetches (the SM's instruction cache holds 32 KB).
         if (lockstep) __syncthreads_and(0);
         // ---- the evaluation site: f, g at x (skipped when x is bit-identical to the last evaluated point) ------
         const bool same = !first && __all_sync(FULL, !mine || x == xlast);
-        if (!same) {
+        if constexpr (SHADOW) {
+            if (!resume && !same && !sc->owner) {
+                // claimant: still wanted? (CLAIMED: the owner's search is running; CONFIRMED: it failed, the task is ours)
+                const unsigned c = sl_load(sc->slot);
+                if (c == sl_ctl(sc->epoch, SL_CONFIRMED)) {
+                    __threadfence();
+                    const ShadowSlot *sl = sc->slot;
+                    nfev += __ldcg(&sl->nfev_after) - __ldcg(&sl->nfev);
+                    o.ns += __ldcg(&sl->ns_after) - __ldcg(&sl->ns); o.nv += __ldcg(&sl->nv_after) - __ldcg(&sl->nv);
+                    o.nc += __ldcg(&sl->nc_after) - __ldcg(&sl->nc);
+                    sc->nanos_base = __ldcg(&sl->nanos_after);
+                    sc->owner = true; sc->published = false;
+                } else if (c != sl_ctl(sc->epoch, SL_CLAIMED)) { o.status = ST_SUPERSEDED; return; }
+            }
+        }
+        if (!same && !resume) {
             EvalOut ev;
             eval_fg<MODE>(P, map, m, M, lane, x, true, ev);
             o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
+            if constexpr (SHADOW) {
+                if (ev.status) { st = ev.status; goto done; }      // the exit below handles requests and pending verdicts
+            }
             if (ev.status) { o.status = ev.status; o.nit = nit; o.nfev = nfev; o.x = x; return; }
             f = ev.f; g = mine ? ev.g : 0.0; nfev++; xlast = x;
 #pragma unroll
             for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
         }
         bool new_dir;
-        if (first) {
+        if (SHADOW && resume) { resume = false; new_dir = true; }
+        else if (first) {
             first = false;
             if (warp_max(fabs(g)) <= pgtol) { st = 1; break; }
             new_dir = true;
@@ -188,6 +259,12 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
             if (dcsrch_step(ls, stp, f, gd) == 0) new_dir = false;        // FG: another trial point
             else {
                 // ---- the line search accepted the last evaluated point ---------------------------------------
+                if constexpr (SHADOW) {
+                    if (sc->owner && sc->published) {       // this epoch is over: a claimant sees the change and stops
+                        if (lane == 0) atomicExch(&sc->slot->ctl, sl_ctl(sc->epoch, SL_IDLE));
+                        sc->published = false;
+                    }
+                }
                 nit++;
                 if (cancel_mask && (*reinterpret_cast<const volatile unsigned *>(cancel_word) & cancel_mask)) {
                     st = ST_CANCELLED; break;
@@ -238,6 +315,24 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
                 const double dnorm = sqrt(warp_sum(d * d));
                 stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
                 t = x; r = g; fold = f;
+                if constexpr (SHADOW) {
+                    if (sc->owner && col > 0) {
+                        ShadowSlot *sl = sc->slot;
+                        if (mine) { sl->x[lane] = x; sl->g[lane] = g; }
+                        if (lane < 4) sl->costs[lane] = o.costs[lane];
+                        if (lane == 0) {
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            sl->f = f; sl->nit = nit; sl->nfev = nfev; sl->ns = o.ns; sl->nv = o.nv; sl->nc = o.nc;
+                            sl->nanos = sc->nanos_base + (now - sc->t_start);
+                        }
+                        __threadfence();
+                        __syncwarp();
+                        sc->epoch++;
+                        if (lane == 0) atomicExch(&sl->ctl, sl_ctl(sc->epoch, SL_REQUESTED));
+                        sc->published = true;
+                    }
+                }
                 gd = warp_sum(g * d);
                 gdold = gd;
                 ifun = 0;
@@ -247,6 +342,29 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
             ifun++;
             if (ifun - 1 < maxls) break;                                    // evaluate the trial point
             // ---- failed search: restore the iterate; ABNORMAL if the memory is already empty ------------------
+            if constexpr (SHADOW) {
+                if (sc->owner && sc->published) {
+                    sc->published = false;
+                    ShadowSlot *sl = sc->slot;
+                    unsigned old = 0;
+                    if (lane == 0) old = atomicCAS(&sl->ctl, sl_ctl(sc->epoch, SL_REQUESTED), sl_ctl(sc->epoch, SL_IDLE));
+                    old = __shfl_sync(FULL, old, 0);
+                    if (old != sl_ctl(sc->epoch, SL_REQUESTED)) {
+                        // CLAIMED: the claimant has been computing this restart; give it the task and retire
+                        if (lane == 0) {
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            sl->nfev_after = nfev; sl->ns_after = o.ns; sl->nv_after = o.nv; sl->nc_after = o.nc;
+                            sl->nanos_after = sc->nanos_base + (now - sc->t_start);
+                            __threadfence();
+                            atomicExch(&sl->ctl, sl_ctl(sc->epoch, SL_CONFIRMED));
+                        }
+                        __syncwarp();
+                        o.status = ST_HANDED_OFF;
+                        return;
+                    }
+                }
+            }
             x = t; g = r; f = fold;
             if (col == 0) { st = 2; goto done; }
             col = 0; head = 0; theta = 1.0;
@@ -255,6 +373,32 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
         x = (stp == 1.0) ? (t + d) : (stp * d + t);
     }
 done:
+    if constexpr (SHADOW) {
+        if (sc->owner && sc->published) {           // exits other than accept/fail (exception, cancel): withdraw the request
+            if (lane == 0) atomicExch(&sc->slot->ctl, sl_ctl(sc->epoch, SL_IDLE));
+            sc->published = false;
+        }
+        while (!sc->owner) {
+            // finished while still speculative: wait for the owner's verdict (it runs on its own resident warp)
+            const unsigned c = sl_load(sc->slot);
+            if (c == sl_ctl(sc->epoch, SL_CONFIRMED)) {
+                __threadfence();
+                const ShadowSlot *sl = sc->slot;
+                nfev += __ldcg(&sl->nfev_after) - __ldcg(&sl->nfev);
+                o.ns += __ldcg(&sl->ns_after) - __ldcg(&sl->ns); o.nv += __ldcg(&sl->nv_after) - __ldcg(&sl->nv);
+                o.nc += __ldcg(&sl->nc_after) - __ldcg(&sl->nc);
+                sc->nanos_base = __ldcg(&sl->nanos_after);
+                sc->owner = true;
+                break;
+            }
+            if (c != sl_ctl(sc->epoch, SL_CLAIMED)) { o.status = ST_SUPERSEDED; return; }
+            if (cancel_mask && (*reinterpret_cast<const volatile unsigned *>(cancel_word) & cancel_mask)) {
+                o.status = ST_SUPERSEDED;           // the owner stops at its own cancel check and reports the task
+                return;
+            }
+            __nanosleep(200);
+        }
+    }
     o.x = x; o.status = st; o.nit = nit; o.nfev = nfev;
 }
 

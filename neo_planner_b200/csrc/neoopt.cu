@@ -51,6 +51,9 @@ struct OptArgs {
     double *x, *ts, *coeffs, *costs;
     int32_t *status, *ok, *attempt, *nit, *runs, *nfev;
     long long *work;
+    // speculative restarts (experimental, SHADOW instantiations only; appended so that the other fields keep their offsets)
+    ShadowSlot *slots;           // (A*B), zeroed per launch
+    unsigned int *n_resolved;    // problems resolved so far (the idle phase ends when it reaches B)
 };
 
 // A problem is resolved once its lowest accepted attempt has all earlier attempts finished, or all attempts finished.
@@ -73,7 +76,9 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // MINB: CTAs per SM the register allocation is sized for. 2 (231 registers) is fastest when the launch is bound by the
 // longest chain of evaluations (few problems per SM); 3 (168 registers, 12 warps per SM) gives more throughput once
 // every SM has a queue of problems (launch_optimize picks by batch size; the arithmetic is the same).
-template <int MODE, int MC, int MINB>
+// SHADOW (experimental, NEO_SHADOW=1, small launches only): warps that find the queue empty serve restart requests of
+// running tasks (lbfgs_warp.cuh, protocol checked on the CPU in oracle/shadow_sim.c) until every problem is resolved.
+template <int MODE, int MC, int MINB, bool SHADOW = false>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
@@ -86,9 +91,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
         unsigned int tid = 0;
         if (lane == 0) tid = atomicAdd(a.counter, 1u);
         tid = __shfl_sync(FULL, tid, 0);
+        bool as_claimant = false;
+        unsigned claimed_epoch = 0;
         if (tid >= total) {
-            if (a.lockstep) while (!__syncthreads_and(1)) { }      // keep meeting the busy warps until all are idle
-            break;
+            if constexpr (SHADOW) {
+                // idle phase: look for a restart request (lanes scan the slots' control words), claim it with a CAS
+                unsigned scan = ((blockIdx.x * WARPS_PER_CTA + warp) * 2654435761u) % total;
+                for (;;) {
+                    if (*reinterpret_cast<volatile unsigned *>(a.n_resolved) >= (unsigned)a.B) break;
+                    for (unsigned k = 0; k < total && !as_claimant; k += 32) {
+                        const unsigned t = (scan + k + lane) % total;
+                        const unsigned c = k + lane < total ? sl_load(a.slots + t) : 0u;
+                        const unsigned want = __ballot_sync(FULL, (c & 3u) == SL_REQUESTED);
+                        if (!want) continue;
+                        const int src = __ffs(want) - 1;
+                        const unsigned t_sel = __shfl_sync(FULL, t, src), c_sel = __shfl_sync(FULL, c, src);
+                        unsigned got = 0;
+                        if (lane == 0) got = atomicCAS(&a.slots[t_sel].ctl, c_sel, (c_sel & ~3u) | SL_CLAIMED) == c_sel;
+                        got = __shfl_sync(FULL, got, 0);
+                        if (got) { tid = t_sel; claimed_epoch = c_sel >> 2; as_claimant = true; }
+                    }
+                    if (as_claimant) break;
+                    scan = (scan + 7919u) % total;
+                    __nanosleep(500);
+                }
+                if (!as_claimant) break;
+            } else {
+                if (a.lockstep) while (!__syncthreads_and(1)) { }      // keep meeting the busy warps until all are idle
+                break;
+            }
         }
         const int at = (int)(tid / (unsigned)a.B);
         const size_t b = tid - (unsigned)at * (unsigned)a.B;
@@ -113,7 +144,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
             OptOut o;
             o.status = st0; o.nit = 0; o.nfev = 0; o.ns = o.nv = o.nc = 0; o.x = 0.0;
             o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
-            if (!st0) lbfgsb_warp<MODE>(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok, a.lockstep != 0);   // else map_T2tau raised (EP:209)
+            ShadowCtx sc;
+            if constexpr (SHADOW) {
+                sc.slot = a.slots + tid; sc.epoch = claimed_epoch; sc.owner = !as_claimant; sc.published = false;
+                sc.t_start = t_start; sc.nanos_base = 0;
+                if (as_claimant) st0 = 0;
+            }
+            if (!st0) lbfgsb_warp<MODE, SHADOW>(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok, a.lockstep != 0, SHADOW ? &sc : nullptr);   // else map_T2tau raised (EP:209)
+            if constexpr (SHADOW) {
+                // a retired owner or an unneeded claimant reports nothing: the task's current owner will
+                if (o.status == ST_HANDED_OFF || o.status == ST_SUPERSEDED) continue;
+                t_start -= sc.nanos_base;               // time earlier owners of this task spent on it
+            }
             if (o.status != ST_CANCELLED) {
                 const bool completed = o.status < NEO_ST_OVERFLOW;             // minimize() returned (EP:213-233)
                 const bool accepted = completed && !(o.costs[3] * P.w3 > P.collision_cost_tol);   // EP:235-237
@@ -130,6 +172,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
                 if (accepted) bits |= 1u << (8 + at);
                 __threadfence();
             }
+        } else if constexpr (SHADOW) {
+            if (as_claimant) continue;                  // claimed a task that is no longer needed: nothing to report
         }
         __syncwarp();
         unsigned old = 0;
@@ -178,6 +222,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
             if (a.work) { a.work[b * 4] = ns; a.work[b * 4 + 1] = nv; a.work[b * 4 + 2] = nc; a.work[b * 4 + 3] = nanos; }
         }
         __syncwarp();
+        if constexpr (SHADOW) {
+            __threadfence();
+            if (lane == 0) atomicAdd(a.n_resolved, 1u);
+        }
     }
 }
 
@@ -327,6 +375,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    int shadow = 0;                  // EXPERIMENTAL (env NEO_SHADOW = 1): speculative restarts in small M = 3 launches
     int staged = -1;                 // development switch (env NEO_STAGED = 0 | 1; default -1: by shared-memory fit)
     int min_ctas = 0;                // development switch (env NEO_MIN_CTAS_FORCE = 2 | 3): overrides the choice by batch size
     int lockstep = 0;                // development switch (env NEO_LOCKSTEP at neo_create): CTA-level lockstep, see k_optimize
@@ -418,6 +467,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     if (const char *e = getenv("NEO_LOCKSTEP")) h->lockstep = atoi(e) != 0;
     if (const char *e = getenv("NEO_MIN_CTAS_FORCE")) h->min_ctas = atoi(e);
     if (const char *e = getenv("NEO_STAGED")) h->staged = atoi(e) != 0 ? 1 : 0;
+    if (const char *e = getenv("NEO_SHADOW")) h->shadow = atoi(e) != 0;
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
     bool good = cudaSetDevice(device) == cudaSuccess &&
@@ -729,6 +779,9 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     }
 #undef NEO_K
 #undef NEO_KP
+    // EXPERIMENTAL: speculative restarts (lbfgs_warp.cuh) -- latency-bound launches of the shipped piece count only
+    const bool shadow = h->shadow && !packed && !h->lockstep && a.M == 3 && (size_t)a.B * a.max_attempts <= 16384;
+    if (shadow) kern = k_optimize<SAMPLE_BY_PIECE, 3, NEO_MIN_CTAS, true>;
     int rc = prep_kernel(h, kern, a.M, &occ, staged);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
@@ -745,6 +798,12 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.maps = h->d_maps;
     a.counter = h->d_counter;
     a.lockstep = h->lockstep;
+    a.slots = nullptr; a.n_resolved = h->d_counter + 1;
+    if (shadow) {
+        if ((rc = dev_buf(h, 8, sizeof(ShadowSlot) * tasks, (void **)&a.slots))) return rc;
+        CK(cudaMemsetAsync(a.slots, 0, sizeof(ShadowSlot) * tasks, st));
+        CK(cudaMemsetAsync(a.n_resolved, 0, sizeof(unsigned int), st));
+    }
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
     kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M, staged), st>>>(dev_params(h->cfg), a);
