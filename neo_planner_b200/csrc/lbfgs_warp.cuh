@@ -169,6 +169,8 @@ struct ShadowSlot {                  // one per task (attempt * B + problem), ze
 
 struct ShadowCtx {                   // warp-uniform
     ShadowSlot *slot;
+    unsigned *req_word;              // discovery bitmap (one bit per task with a request out; ctl stays authoritative)
+    unsigned req_bit;
     unsigned epoch;                  // owner: last published epoch; claimant: the epoch it claimed
     bool owner;                      // true: owns the task and publishes; false: speculative
     bool published;                  // owner: the running line search has a request out
@@ -261,7 +263,7 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
                 // ---- the line search accepted the last evaluated point ---------------------------------------
                 if constexpr (SHADOW) {
                     if (sc->owner && sc->published) {       // this epoch is over: a claimant sees the change and stops
-                        if (lane == 0) atomicExch(&sc->slot->ctl, sl_ctl(sc->epoch, SL_IDLE));
+                        if (lane == 0) { atomicExch(&sc->slot->ctl, sl_ctl(sc->epoch, SL_IDLE)); atomicAnd(sc->req_word, ~sc->req_bit); }
                         sc->published = false;
                     }
                 }
@@ -329,7 +331,7 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
                         __threadfence();
                         __syncwarp();
                         sc->epoch++;
-                        if (lane == 0) atomicExch(&sl->ctl, sl_ctl(sc->epoch, SL_REQUESTED));
+                        if (lane == 0) { atomicExch(&sl->ctl, sl_ctl(sc->epoch, SL_REQUESTED)); atomicOr(sc->req_word, sc->req_bit); }
                         sc->published = true;
                     }
                 }
@@ -347,7 +349,10 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
                     sc->published = false;
                     ShadowSlot *sl = sc->slot;
                     unsigned old = 0;
-                    if (lane == 0) old = atomicCAS(&sl->ctl, sl_ctl(sc->epoch, SL_REQUESTED), sl_ctl(sc->epoch, SL_IDLE));
+                    if (lane == 0) {
+                        old = atomicCAS(&sl->ctl, sl_ctl(sc->epoch, SL_REQUESTED), sl_ctl(sc->epoch, SL_IDLE));
+                        atomicAnd(sc->req_word, ~sc->req_bit);
+                    }
                     old = __shfl_sync(FULL, old, 0);
                     if (old != sl_ctl(sc->epoch, SL_REQUESTED)) {
                         // CLAIMED: the claimant has been computing this restart; give it the task and retire
@@ -375,7 +380,7 @@ __device__ __forceinline__ void lbfgsb_warp(const DevParams &P, const MapView &m
 done:
     if constexpr (SHADOW) {
         if (sc->owner && sc->published) {           // exits other than accept/fail (exception, cancel): withdraw the request
-            if (lane == 0) atomicExch(&sc->slot->ctl, sl_ctl(sc->epoch, SL_IDLE));
+            if (lane == 0) { atomicExch(&sc->slot->ctl, sl_ctl(sc->epoch, SL_IDLE)); atomicAnd(sc->req_word, ~sc->req_bit); }
             sc->published = false;
         }
         while (!sc->owner) {

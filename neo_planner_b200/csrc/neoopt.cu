@@ -54,6 +54,7 @@ struct OptArgs {
     // speculative restarts (experimental, SHADOW instantiations only; appended so that the other fields keep their offsets)
     ShadowSlot *slots;           // (A*B), zeroed per launch
     unsigned int *n_resolved;    // problems resolved so far (the idle phase ends when it reaches B)
+    unsigned int *req_bits;      // ceil(A*B / 32) words: tasks with a restart request out (discovery only)
 };
 
 // A problem is resolved once its lowest accepted attempt has all earlier attempts finished, or all attempts finished.
@@ -95,24 +96,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
         unsigned claimed_epoch = 0;
         if (tid >= total) {
             if constexpr (SHADOW) {
-                // idle phase: look for a restart request (lanes scan the slots' control words), claim it with a CAS
-                unsigned scan = ((blockIdx.x * WARPS_PER_CTA + warp) * 2654435761u) % total;
+                // idle phase: look for a restart request (lanes scan the request bitmap), claim it with a CAS on its slot
+                const unsigned nwords = (total + 31u) / 32u;
+                unsigned rot = (blockIdx.x * WARPS_PER_CTA + warp) % nwords;
                 for (;;) {
                     if (*reinterpret_cast<volatile unsigned *>(a.n_resolved) >= (unsigned)a.B) break;
-                    for (unsigned k = 0; k < total && !as_claimant; k += 32) {
-                        const unsigned t = (scan + k + lane) % total;
-                        const unsigned c = k + lane < total ? sl_load(a.slots + t) : 0u;
-                        const unsigned want = __ballot_sync(FULL, (c & 3u) == SL_REQUESTED);
+                    for (unsigned w0 = 0; w0 < nwords && !as_claimant; w0 += 32) {
+                        const unsigned wi = (w0 + lane + rot) % nwords;
+                        const unsigned word = w0 + lane < nwords ? *reinterpret_cast<volatile unsigned *>(a.req_bits + wi) : 0u;
+                        const unsigned want = __ballot_sync(FULL, word != 0u);
                         if (!want) continue;
                         const int src = __ffs(want) - 1;
-                        const unsigned t_sel = __shfl_sync(FULL, t, src), c_sel = __shfl_sync(FULL, c, src);
-                        unsigned got = 0;
-                        if (lane == 0) got = atomicCAS(&a.slots[t_sel].ctl, c_sel, (c_sel & ~3u) | SL_CLAIMED) == c_sel;
-                        got = __shfl_sync(FULL, got, 0);
+                        const unsigned w_sel = __shfl_sync(FULL, wi, src), bits_sel = __shfl_sync(FULL, word, src);
+                        const unsigned t_sel = w_sel * 32u + (unsigned)(__ffs(bits_sel) - 1);
+                        if (t_sel >= total) continue;
+                        unsigned c_sel = 0, got = 0;
+                        if (lane == 0) {
+                            c_sel = sl_load(a.slots + t_sel);
+                            if ((c_sel & 3u) == SL_REQUESTED)
+                                got = atomicCAS(&a.slots[t_sel].ctl, c_sel, (c_sel & ~3u) | SL_CLAIMED) == c_sel;
+                            atomicAnd(a.req_bits + w_sel, ~(1u << (t_sel & 31u)));      // taken, or stale: either way not pending
+                        }
+                        c_sel = __shfl_sync(FULL, c_sel, 0); got = __shfl_sync(FULL, got, 0);
                         if (got) { tid = t_sel; claimed_epoch = c_sel >> 2; as_claimant = true; }
                     }
                     if (as_claimant) break;
-                    scan = (scan + 7919u) % total;
+                    rot = (rot + 1u) % nwords;
                     __nanosleep(500);
                 }
                 if (!as_claimant) break;
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
             ShadowCtx sc;
             if constexpr (SHADOW) {
                 sc.slot = a.slots + tid; sc.epoch = claimed_epoch; sc.owner = !as_claimant; sc.published = false;
+                sc.req_word = a.req_bits + (tid >> 5); sc.req_bit = 1u << (tid & 31u);
                 sc.t_start = t_start; sc.nanos_base = 0;
                 if (as_claimant) st0 = 0;
             }
@@ -798,10 +808,13 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.maps = h->d_maps;
     a.counter = h->d_counter;
     a.lockstep = h->lockstep;
-    a.slots = nullptr; a.n_resolved = h->d_counter + 1;
+    a.slots = nullptr; a.n_resolved = h->d_counter + 1; a.req_bits = nullptr;
     if (shadow) {
-        if ((rc = dev_buf(h, 8, sizeof(ShadowSlot) * tasks, (void **)&a.slots))) return rc;
-        CK(cudaMemsetAsync(a.slots, 0, sizeof(ShadowSlot) * tasks, st));
+        const size_t words = (tasks + 31) / 32, slot_bytes = (sizeof(ShadowSlot) * tasks + 255) & ~(size_t)255;
+        char *sb;
+        if ((rc = dev_buf(h, 8, slot_bytes + sizeof(unsigned) * words, (void **)&sb))) return rc;
+        a.slots = (ShadowSlot *)sb; a.req_bits = (unsigned *)(sb + slot_bytes);
+        CK(cudaMemsetAsync(sb, 0, slot_bytes + sizeof(unsigned) * words, st));
         CK(cudaMemsetAsync(a.n_resolved, 0, sizeof(unsigned int), st));
     }
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
