@@ -68,3 +68,34 @@ def test_kernel_source_on_host_edge_cases(golden, sim):
     assert np.array_equal(out['path'][0, :1], g['lost_path']) and np.array_equal(out['pruned'][0], g['lost_pruned'])
     out = sim(gm, [[2.5, 2.5], [-20.0, 0.0], [2.5, 2.5]], [[2.6, 2.7], [3.0, 3.0], [10.5, 6.5]], max_closed=10)
     assert out['status'].tolist() == [0, 2, 3] and out['path_len'].tolist() == [1, 0, 0]
+
+
+def test_kernel_source_on_host_random_maps(sim):
+    """Property test (hypothesis): random small maps with random obstacles, resolutions and origins, start/target anywhere
+    on or around the map (blocked, unreachable and out-of-grid cases included): the device source run on the host and
+    the checker agree on status, path, pruned key nodes and expansion count."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from oracle import astar_ref
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.integers(4, 14), st.integers(4, 14), st.sampled_from([0.5, 1.0, 2.0, 0.25]), st.floats(-3, 3), st.floats(-3, 3),
+           st.floats(0.0, 0.35), st.integers(0, 10 ** 6))
+    def run(H, W, res, ox, oy, density, seed):
+        rng = np.random.default_rng(seed)
+        occ = np.where(rng.random((H, W)) < density, 100, 0).astype(np.int8)
+        gm = minco_ref.GridMap(occ, H, W, res, ox, oy)
+        lo = np.array([ox - 6.0, oy - 6.0]); hi = np.array([ox + W * res + 6.0, oy + H * res + 6.0])
+        start = rng.uniform(lo, hi, size=(3, 2)); target = rng.uniform(lo, hi, size=(3, 2))
+        out = sim(gm, start, target, max_path=2048, open_fast=int(rng.choice([3, 64, 512])))
+        grid = astar_ref.SearchGrid(gm)
+        for i in range(3):
+            sx, sy = grid.cell_of(start[i, 0], start[i, 1])
+            if not (0 <= sx < grid.W and 0 <= sy < grid.H):
+                assert out['status'][i] == 2 and out['path_len'][i] == 0      # rejected up front (reference: index aliasing)
+                continue
+            path, found, nclosed = astar_ref.astar(gm, start[i], target[i])
+            four, _, _ = astar_ref.prune(gm, path)
+            assert out['status'][i] == (0 if found else 1) and out['closed'][i] == nclosed
+            assert out['path_len'][i] == len(path) and np.array_equal(out['path'][i, :len(path)], np.array(path))
+            assert np.array_equal(out['pruned'][i], np.array(four))
+    run()
