@@ -53,7 +53,6 @@ def lib():
         _lib = C.CDLL(build())
         _lib.orc_get_coeffs.restype = C.c_int
         _lib.orc_sample_count.restype = C.c_int
-        _lib.orc_set_trace.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_sample_count.argtypes = [C.c_int, C.c_void_p, C.c_double]
         _lib.orc_sample.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         _lib.orc_esdf_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -143,6 +142,89 @@ def plan_batch(params, omap, M, head, tail, q0, ts0, retry_q=None, retry_ts=None
                          C.c_int(max_attempts), _p(out['x']), _p(out['ts']), _p(out['coeffs']), _p(out['costs']),
                          _p(out['status']), _p(out['ok']), _p(out['attempt']), _p(out['nit']), _p(out['runs']),
                          _p(out['nfev']))
+    return out
+
+
+class Result(C.Structure):
+    _fields_ = [('x', C.c_double * 46), ('costs', C.c_double * 4), ('f', C.c_double), ('status', C.c_int),
+                ('nit', C.c_int), ('nfev', C.c_int)]
+
+
+FG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                    C.POINTER(C.c_double))
+
+
+def lbfgsb_cb(fg, x0):
+    """The C restatement of scipy's L-BFGS-B around a Python evaluator fg(x) -> (f, g). Returns (x, nit, nfev, status)."""
+    x0 = f64(x0); n = x0.size
+
+    def tramp(_ctx, n_, xp, fp, gp, cp):
+        x = np.array([xp[i] for i in range(n_)])
+        try:
+            f, g = fg(x)
+        except OverflowError:
+            return 4
+        except (ValueError, ZeroDivisionError):
+            return 5
+        fp[0] = float(f)
+        for i in range(n_):
+            gp[i] = float(g[i])
+        for i in range(4):
+            cp[i] = 0.0
+        return 0
+    res = Result()
+    cb = FG_FN(tramp)
+    st = lib().orc_lbfgsb_cb(C.c_int(n), _p(x0), cb, None, C.byref(res))
+    return np.array(res.x[:n]), res.nit, res.nfev, st
+
+
+def lbfgsb_traced(params, omap, M, head, tail, x0, cap=4096):
+    """One minimize() call of the checker with every evaluation recorded. Returns dict(x, nit, nfev, status, xs, fs, gs)."""
+    x0 = f64(x0); n = x0.size
+    head = f64(pad_state(head)); tail = f64(pad_state(tail))
+    xs = np.zeros((cap, n)); fs = np.zeros(cap); gs = np.zeros((cap, n))
+    res = Result()
+    k = lib().orc_lbfgsb_traced(C.byref(params), C.byref(omap.c), C.c_int(M), _p(head), _p(tail), _p(x0), C.byref(res),
+                                C.c_int(cap), _p(xs), _p(fs), _p(gs))
+    return dict(x=np.array(res.x[:n]), nit=res.nit, nfev=res.nfev, status=res.status, costs=np.array(res.costs[:]),
+                xs=xs[:k], fs=fs[:k], gs=gs[:k])
+
+
+def lbfgsb_replay(x0, xs, fs, gs, costs=None, status=None):
+    """Feeds recorded evaluations (the device's) to the checker's optimizer. Returns dict(x, nit, nfev, status,
+    first_bad (-1: every requested point was bit-identical to the recorded one), used)."""
+    x0 = f64(x0); n = x0.size
+    xs = f64(xs).reshape(-1, n); gs = f64(gs).reshape(-1, n); fs = f64(fs)
+    k = xs.shape[0]
+    costs = np.zeros((k, 4)) if costs is None else f64(costs)
+    st = None if status is None else np.ascontiguousarray(status, dtype=np.int32)
+    res = Result(); bad = C.c_int(-1); used = C.c_int(0)
+    rc = lib().orc_lbfgsb_replay(C.c_int(n), _p(x0), C.c_int(k), _p(xs), _p(fs), _p(gs), _p(costs),
+                                 None if st is None else _p(st), C.byref(res), C.byref(bad), C.byref(used))
+    return dict(x=np.array(res.x[:n]), nit=res.nit, nfev=res.nfev, status=rc, first_bad=bad.value, used=used.value,
+                costs=np.array(res.costs[:]))
+
+
+def plan_batch_mt(params, maps, M, head, tail, q0, ts0, retry_q=None, retry_ts=None, max_attempts=1, map_ids=None,
+                  threads=None):
+    """plan_batch over several maps on `threads` host threads (default: all cores). maps: list of OracleMap."""
+    threads = threads or os.cpu_count() or 1
+    q0 = f64(q0); B = q0.shape[0]; n = 2 * (M - 1) + M
+    ts0 = f64(ts0)
+    head = f64(pad_state(head)); tail = f64(pad_state(tail))
+    if max_attempts > 1:
+        retry_q = f64(retry_q); retry_ts = f64(retry_ts)
+        assert retry_q.shape == (B, max_attempts - 1, 2, M - 1)
+    ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+    arr = (C.c_void_p * len(maps))(*[C.addressof(m_.c) for m_ in maps])
+    out = dict(x=np.zeros((B, n)), ts=np.zeros((B, M)), coeffs=np.zeros((B, 6 * M, 2)), costs=np.zeros((B, 4)),
+               status=np.zeros(B, np.int32), ok=np.zeros(B, np.int32), attempt=np.zeros(B, np.int32),
+               nit=np.zeros(B, np.int32), runs=np.zeros(B, np.int32), nfev=np.zeros(B, np.int32))
+    lib().orc_plan_batch_mt(C.byref(params), arr, None if ids is None else _p(ids), C.c_int(B), C.c_int(M), _p(head),
+                            _p(tail), _p(q0), _p(ts0), _p(retry_q) if max_attempts > 1 else None,
+                            _p(retry_ts) if max_attempts > 1 else None, C.c_int(max_attempts), C.c_int(threads),
+                            _p(out['x']), _p(out['ts']), _p(out['coeffs']), _p(out['costs']), _p(out['status']),
+                            _p(out['ok']), _p(out['attempt']), _p(out['nit']), _p(out['runs']), _p(out['nfev']))
     return out
 
 

@@ -624,7 +624,197 @@ static int dcsrch_step(dcs_state *S, double *stp, double f, double g)
     return 0;
 }
 
-static double dotn(int n, const double *a, const double *b) { double s = 0.0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+/* ---- scipy 1.18.1's L-BFGS-B (C port of L-BFGS-B 3.0), unbounded case, restated operation by operation ------------
+ * scipy is a third-party dependency of the reference (call site EP:213-225; not vendored, not pinned by the reference:
+ * README.md:43). Its compiled module calls BLAS/LAPACK from the bundled OpenBLAS 0.3.31 (SkylakeX kernels on the build
+ * machine); the routines below restate the arithmetic of exactly those kernels for the sizes that occur here (vectors of
+ * n <= 31, triangular systems of order <= 20), so that -- fed the same (f, g) values -- this file walks through the same
+ * iterates as scipy BIT FOR BIT. Pinned by tests/test_oracle_golden.py::test_lbfgsb_restatement_bit_identical_to_scipy
+ * (reference-identical Python f/g driven through scipy.optimize.minimize and through orc_lbfgsb_cb).
+ * How each rule was established (against scipy.optimize._lbfgsb.setulb's workspace, call by call) is recorded in
+ * DESIGN.md section 3. The file is compiled with -ffp-contract=off: every fused multiply-add below is an explicit fma().
+ *   ddot   n < 16: s = fma(a_i, b_i, s) in index order. 16 <= n < 32: the first 16 products are rounded, added in four
+ *          lanes ((p_l + p_l+4) + p_l+8) + p_l+12, folded (v0 + v2) + (v1 + v3); the rest continues with fma.
+ *   dnrm2  x87 kernel: squares and their sum in 80-bit extended precision, fsqrt, rounded to double once at the end.
+ *   dpotrf (potf2_U): diagonal a_jj - ddot, sqrt; row to the right y_i -= sum_k a_ki a_kj in the order of the dgemv_t
+ *          kernel (blocks of four rows in lanes, (l0 + l2) + (l1 + l3); 1-3 leftover rows folded as below); times 1/a_jj.
+ *   dtrtrs one right-hand side -> trsv: transposed: (b_i - ddot) / u_ii; not transposed: b_i / u_ii, then fma axpy.
+ *          several right-hand sides -> trsm kernel: blocks of 8, 4, 2, 1 rows; per block first b_i -= sum over the rows
+ *          of earlier blocks (fma from zero), then inside the block b_i *= 1/u_ii and b_k = fma(-b_i, u_ik, b_k).
+ *   loops written out in scipy's own C (formk's inner products, subsm, the projected gradient) are plain mul + add. */
+static double blas_ddot(int n, const double *a, int sa, const double *b, int sb)
+{
+    double s = 0.0;
+    int i = 0;
+    if (n >= 16) {
+        double v[4];
+        for (int l = 0; l < 4; l++)
+            v[l] = ((a[l * sa] * b[l * sb] + a[(4 + l) * sa] * b[(4 + l) * sb]) + a[(8 + l) * sa] * b[(8 + l) * sb]) +
+                   a[(12 + l) * sa] * b[(12 + l) * sb];
+        s = (v[0] + v[2]) + (v[1] + v[3]);
+        i = 16;
+    }
+    for (; i < n; i++) s = fma(a[i * sa], b[i * sb], s);
+    return s;
+}
+
+static double blas_dnrm2(int n, const double *a)
+{
+    long double s = 0.0L;
+    for (int i = 0; i < n; i++) { const long double v = a[i]; s += v * v; }
+    return (double)sqrtl(s);
+}
+
+#define LB_M ORC_HIST
+#define LB_W (2 * LB_M)
+/* upper-triangular factor in a[o..o+n)[o..o+n) of the LB_W x LB_W row-major array; 0 if not positive definite */
+static int lapack_potf2(double (*a)[LB_W], int o, int n)
+{
+    for (int j = 0; j < n; j++) {
+        double ajj = a[o + j][o + j] - blas_ddot(j, &a[o][o + j], LB_W, &a[o][o + j], LB_W);
+        if (!(ajj > 0.0)) return 0;
+        ajj = sqrt(ajj);
+        a[o + j][o + j] = ajj;
+        if (j == n - 1) break;
+        const int m1 = j & ~3, k3 = j - m1;
+        for (int i = j + 1; i < n; i++) {
+#define COL(k) a[o + (k)][o + i]
+#define XJ(k) a[o + (k)][o + j]
+            double v = a[o + j][o + i];
+            if (m1) {
+                double acc[4];
+                for (int l = 0; l < 4; l++) acc[l] = COL(l) * XJ(l);
+                if (m1 == 8) for (int l = 0; l < 4; l++) acc[l] = acc[l] + COL(4 + l) * XJ(4 + l);
+                v = v - ((acc[0] + acc[2]) + (acc[1] + acc[3]));
+            }
+            if (k3 == 1) v = fma(COL(m1), -XJ(m1), v);
+            else if (k3 == 2) v = v + fma(COL(m1), -XJ(m1), COL(m1 + 1) * -XJ(m1 + 1));
+            else if (k3 == 3) v = v + fma(COL(m1 + 2), -XJ(m1 + 2), fma(COL(m1), -XJ(m1), COL(m1 + 1) * -XJ(m1 + 1)));
+            a[o + j][o + i] = v;
+#undef COL
+#undef XJ
+        }
+        const double r = 1.0 / ajj;
+        for (int i = j + 1; i < n; i++) a[o + j][o + i] = a[o + j][o + i] * r;
+    }
+    return 1;
+}
+
+/* u = a[0..n)[0..n) upper. b: contiguous vector. */
+static void blas_trsv_T(double (*u)[LB_W], int n, double *b)
+{
+    for (int i = 0; i < n; i++) {
+        if (i > 0) b[i] = b[i] - blas_ddot(i, &u[0][i], LB_W, b, 1);
+        b[i] = b[i] / u[i][i];
+    }
+}
+
+static void blas_trsv_N(double (*u)[LB_W], int n, double *b)
+{
+    for (int i = n - 1; i >= 0; i--) {
+        b[i] = b[i] / u[i][i];
+        const double t = -b[i];
+        for (int k = 0; k < i; k++) b[k] = fma(t, u[k][i], b[k]);
+    }
+}
+
+/* u^T X = B for the nrhs >= 2 columns c0.. of the same array (rows 0..n-1), n <= 15 */
+static void blas_trsm_LT(double (*a)[LB_W], int n, int c0, int nrhs)
+{
+    for (int c = c0; c < c0 + nrhs; c++) {
+        int kk = 0;
+        for (int bs = 8; bs > 0; bs >>= 1) {
+            if (!(n & bs)) continue;
+            if (kk > 0)
+                for (int i = kk; i < kk + bs; i++) {
+                    double acc = 0.0;
+                    for (int k = 0; k < kk; k++) acc = fma(a[k][i], a[k][c], acc);
+                    a[i][c] = a[i][c] - acc;
+                }
+            for (int i = kk; i < kk + bs; i++) {
+                a[i][c] = a[i][c] * (1.0 / a[i][i]);
+                for (int k = i + 1; k < kk + bs; k++) a[k][c] = fma(-a[i][c], a[i][k], a[k][c]);
+            }
+            kk += bs;
+        }
+    }
+}
+
+/* limited-memory matrices (all variables free): pairs oldest first */
+typedef struct {
+    int n, col, iupdat;
+    double theta;
+    double ws[LB_M][ORC_MAXN], wy[LB_M][ORC_MAXN];
+    double dr[LB_M];                 /* diagonal of S'Y as stored by matupd: (gd - gdold) * stp */
+    double yy[LB_M][LB_M];           /* formk's wn1 block (1,1): Y'Y, lower triangle */
+    double rz[LB_M][LB_M];           /* formk's wn1 block (2,1): upper triangle of S'Y (its own inner products) */
+    double wn[LB_W][LB_W];           /* the factored middle matrix */
+} lb_mem;
+
+static double loop_dot(int n, const double *a, const double *b) { double s = 0.0; for (int i = 0; i < n; i++) s = s + a[i] * b[i]; return s; }
+
+static void lb_reset(lb_mem *C, int n) { C->n = n; C->col = 0; C->iupdat = 0; C->theta = 1.0; }
+
+static void lb_update(lb_mem *C, const double *s, const double *y, double rr, double dr)
+{
+    const int n = C->n;
+    C->iupdat++;
+    if (C->iupdat <= LB_M) C->col = C->iupdat;
+    else {
+        memmove(C->ws[0], C->ws[1], sizeof(double) * (LB_M - 1) * ORC_MAXN);
+        memmove(C->wy[0], C->wy[1], sizeof(double) * (LB_M - 1) * ORC_MAXN);
+        for (int j = 0; j < LB_M - 1; j++) {
+            C->dr[j] = C->dr[j + 1];
+            for (int i = j; i < LB_M - 1; i++) C->yy[i][j] = C->yy[i + 1][j + 1];
+            for (int i = 0; i < LB_M - 1; i++) C->rz[i][j] = C->rz[i + 1][j + 1];
+        }
+    }
+    const int col = C->col;
+    memcpy(C->ws[col - 1], s, sizeof(double) * n); memcpy(C->wy[col - 1], y, sizeof(double) * n);
+    C->theta = rr / dr;
+    C->dr[col - 1] = dr;
+    for (int j = 0; j < col; j++) C->yy[col - 1][j] = loop_dot(n, C->wy[col - 1], C->wy[j]);
+    for (int i = 0; i < col; i++) C->rz[i][col - 1] = loop_dot(n, C->ws[i], C->wy[col - 1]);
+}
+
+/* formk: assemble and factor; 0 if a Cholesky factorisation fails (scipy then drops the memory) */
+static int lb_factor(lb_mem *C)
+{
+    const int col = C->col;
+    const double theta = C->theta;
+    double (*wn)[LB_W] = C->wn;
+    for (int iy = 0; iy < col; iy++) {
+        const int is = col + iy;
+        for (int jy = 0; jy <= iy; jy++) { wn[jy][iy] = C->yy[iy][jy] / theta; wn[col + jy][is] = 0.0 * theta; }
+        for (int jy = 0; jy < iy; jy++) wn[jy][is] = -0.0;
+        for (int jy = iy; jy < col; jy++) wn[jy][is] = C->rz[iy][jy];
+        wn[iy][iy] = wn[iy][iy] + C->dr[iy];
+    }
+    if (!lapack_potf2(wn, 0, col)) return 0;
+    if (col == 1) wn[0][1] = wn[0][1] / wn[0][0];        /* one right-hand side: trsv */
+    else blas_trsm_LT(wn, col, col, col);
+    for (int is = col; is < 2 * col; is++)
+        for (int js = is; js < 2 * col; js++)
+            wn[is][js] = wn[is][js] + blas_ddot(col, &wn[0][is], LB_W, &wn[0][js], LB_W);
+    return lapack_potf2(wn, col, col);
+}
+
+/* subsm with r = -g: the subspace step (added to x by the caller) */
+static void lb_step(lb_mem *C, const double *g, double *d)
+{
+    const int col = C->col, n = C->n;
+    const double theta = C->theta;
+    double wv[LB_W];
+    for (int i = 0; i < n; i++) d[i] = -g[i];
+    for (int i = 0; i < col; i++) { wv[i] = loop_dot(n, C->wy[i], d); wv[col + i] = theta * loop_dot(n, C->ws[i], d); }
+    blas_trsv_T(C->wn, 2 * col, wv);
+    for (int i = 0; i < col; i++) wv[i] = -wv[i];
+    blas_trsv_N(C->wn, 2 * col, wv);
+    for (int jy = 0; jy < col; jy++)
+        for (int i = 0; i < n; i++) d[i] = d[i] + C->wy[jy][i] * wv[jy] / theta + C->ws[jy][i] * wv[col + jy];
+    const double it = 1.0 / theta;
+    for (int i = 0; i < n; i++) d[i] = d[i] * it;
+}
 
 typedef struct {
     double x[ORC_MAXN];
@@ -633,86 +823,55 @@ typedef struct {
     int status, nit, nfev;
 } orc_result;
 
-/* Optional trace for offline analysis of the evaluation chain (scripts/analyze_chain.py): one int per line search,
- * evals * 4 + failed * 2 + (memory non-empty at its start), preceded by -1 for every minimize() call. */
-static int *orc_trace_buf = 0;
-static int orc_trace_cap = 0, orc_trace_len = 0;
-void orc_set_trace(int *buf, int cap) { orc_trace_buf = buf; orc_trace_cap = cap; orc_trace_len = 0; }
-int orc_trace_count(void) { return orc_trace_len; }
-static void orc_trace_put(int v) { if (orc_trace_buf && orc_trace_len < orc_trace_cap) orc_trace_buf[orc_trace_len++] = v; }
+/* f, g (and the four unweighted cost terms) at x; returns 0 or the status the reference's exception maps to */
+typedef int (*orc_fg_fn)(void *ctx, int n, const double *x, double *f, double *g, double *costs);
+enum { ORC_REPLAY_DIVERGED = 8 };
 
-/* Restart states for the analysis of speculative restarts: what the optimizer would continue
- * from if the line search that is about to start failed -- captured at the start of every line search that has memory. */
-typedef struct {
-    double x[ORC_MAXN], g[ORC_MAXN], f, costs[4];
-    int nit, nfev;          /* counters at the start of the line search */
-    int failed, nfev_after; /* set when that line search failed: evaluations counted up to the failure */
-} orc_restart;
-static orc_restart *orc_snap_buf = 0;
-static int orc_snap_cap = 0, orc_snap_len = 0;
-void orc_set_snapshots(orc_restart *buf, int cap) { orc_snap_buf = buf; orc_snap_cap = cap; orc_snap_len = 0; }
-int orc_snapshot_count(void) { return orc_snap_len; }
+/* Optional recording of every evaluation (x, f, g) of the running minimize() call, for the lockstep tests. */
+typedef struct { int cap, len; double *x, *f, *g; } orc_trace;
+static __thread orc_trace *orc_trace_cur = 0;
 
-/* Hooks for the protocol simulator of speculative restarts (oracle/shadow_sim.c); NULL everywhere else. */
-typedef struct {
-    void *ctx;
-    /* a line search with non-empty memory is about to start from (x, g, f); counters at that moment */
-    void (*ls_start)(void *ctx, int n, const double *x, const double *g, double f, const double *costs, int nit, int nfev);
-    void (*ls_end)(void *ctx);                  /* that search ended without failing (accepted point or exception) */
-    int (*ls_fail)(void *ctx, int nfev, const double *costs);   /* it failed; 1 = a shadow took the task over: retire */
-    int (*poll)(void *ctx);                     /* before every evaluation; 1 = stop (cancelled / superseded) */
-} orc_hooks;
-static __thread const orc_hooks *orc_hooks_cur = 0;
-enum { ORC_STOPPED = 8, ORC_HANDED_OFF = 9 };
-
-/* The L-BFGS-B iteration from a given iterate (x, f, g known, memory empty). plan_once's minimize() call:
- * tol=1e-4 -> ftol = gtol = 1e-4; maxcor 10; maxls 20; maxiter = maxfun = 15000. have_xl: x is the last evaluated point. */
-static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
-                       const double *x_in, const double *g_in, double f, int nit, int nfev, int have_xl, orc_result *out)
+/* plan_once's minimize() call: tol=1e-4 -> ftol = gtol = 1e-4; maxcor 10; maxls 20; maxiter = maxfun = 15000. */
+static int lbfgsb_run(int n, const double *x0, orc_fg_fn fg, void *ctx, orc_result *out)
 {
-    const int n = ORC_D * (M - 1) + M, m = ORC_HIST, maxls = 20, maxiter = 15000, maxfun = 15000;
+    const int maxls = 20, maxiter = 15000, maxfun = 15000;
     const double pgtol = 1e-4, ftol = 1e-4, epsmch = DBL_EPSILON;
     const double tol = (ftol / epsmch) * epsmch;
-    double x[ORC_MAXN], g[ORC_MAXN], d[ORC_MAXN], t[ORC_MAXN], r[ORC_MAXN], xl[ORC_MAXN], xn[ORC_MAXN];
-    double S[ORC_HIST][ORC_MAXN], Y[ORC_HIST][ORC_MAXN], rho[ORC_HIST], al[ORC_HIST];
-    double costs[4], fold, theta = 1.0;
-    int col = 0, head_i = 0, st;
-    memcpy(x, x_in, sizeof(double) * n); memcpy(g, g_in, sizeof(double) * n);
-    if (have_xl) memcpy(xl, x, sizeof(double) * n);
-    else for (int i = 0; i < n; i++) xl[i] = NAN;      /* a speculative restart does not know the failed search's last trial */
+    double x[ORC_MAXN], g[ORC_MAXN], d[ORC_MAXN], z[ORC_MAXN], t[ORC_MAXN], r[ORC_MAXN], xl[ORC_MAXN], xn[ORC_MAXN];
+    double costs[4] = {0, 0, 0, 0}, f = 0.0, fold;
+    int nit = 0, nfev = 0, st;
+    static __thread lb_mem C;
+    lb_reset(&C, n);
+    memcpy(x, x0, sizeof(double) * n);
+#define LB_EVAL()                                                                                              \
+    do {                                                                                                       \
+        st = fg(ctx, n, x, &f, g, costs);                                                                      \
+        if (st) { out->status = st; out->nit = nit; out->nfev = nfev; memcpy(out->x, x, sizeof(double) * n); return st; } \
+        nfev++; memcpy(xl, x, sizeof(double) * n); memcpy(out->costs, costs, sizeof(costs));                    \
+        if (orc_trace_cur && orc_trace_cur->len < orc_trace_cur->cap) {                                        \
+            orc_trace *T = orc_trace_cur;                                                                      \
+            memcpy(T->x + (size_t)T->len * n, x, sizeof(double) * n); memcpy(T->g + (size_t)T->len * n, g, sizeof(double) * n); \
+            T->f[T->len++] = f;                                                                                \
+        }                                                                                                      \
+    } while (0)
+    LB_EVAL();
     double sbg = 0.0; for (int i = 0; i < n; i++) sbg = fmax(sbg, fabs(g[i]));
     if (sbg <= pgtol) { st = ORC_CONV_PG; goto done; }
     for (;;) {
-        /* search direction d = -H g (two-loop recursion, H0 = I/theta) */
-        for (int i = 0; i < n; i++) d[i] = g[i];
-        for (int k = col - 1; k >= 0; k--) {
-            int j = (head_i + k) % m;
-            al[k] = rho[j] * dotn(n, S[j], d);
-            for (int i = 0; i < n; i++) d[i] -= al[k] * Y[j][i];
+        /* search direction: Cauchy point x - g with an empty memory (theta = 1), else the subspace step; d = z - x */
+        if (C.col == 0) for (int i = 0; i < n; i++) z[i] = x[i] - g[i];
+        else {
+            if (!lb_factor(&C)) { lb_reset(&C, n); continue; }
+            lb_step(&C, g, d);
+            for (int i = 0; i < n; i++) z[i] = x[i] + d[i];
         }
-        if (theta != 1.0) for (int i = 0; i < n; i++) d[i] /= theta;
-        for (int k = 0; k < col; k++) {
-            int j = (head_i + k) % m;
-            double b = rho[j] * dotn(n, Y[j], d);
-            for (int i = 0; i < n; i++) d[i] += (al[k] - b) * S[j][i];
-        }
-        for (int i = 0; i < n; i++) d[i] = -d[i];
+        for (int i = 0; i < n; i++) d[i] = z[i] - x[i];
         /* lnsrlb */
-        double dnorm = sqrt(dotn(n, d, d));
+        const double dnorm = blas_dnrm2(n, d);
         double stp = (nit == 0) ? fmin(1.0 / dnorm, LS_STPMAX) : 1.0;
         memcpy(t, x, sizeof(double) * n); memcpy(r, g, sizeof(double) * n); fold = f;
-        double gd = dotn(n, g, d), gdold = gd;
-        int fail = 0, snap = -1;
-        const int nfev_ls = nfev;
-        const orc_hooks *hk = orc_hooks_cur;
-        const int published = hk && col > 0;
-        if (published) hk->ls_start(hk->ctx, n, x, g, f, out->costs, nit, nfev);
-        if (col > 0 && orc_snap_buf && orc_snap_len < orc_snap_cap) {
-            orc_restart *rs = &orc_snap_buf[snap = orc_snap_len++];
-            memcpy(rs->x, x, sizeof(double) * n); memcpy(rs->g, g, sizeof(double) * n);
-            rs->f = f; memcpy(rs->costs, out->costs, sizeof(rs->costs));
-            rs->nit = nit; rs->nfev = nfev; rs->failed = 0; rs->nfev_after = 0;
-        }
+        double gd = blas_ddot(n, g, 1, d, 1), gdold = gd;
+        int fail = 0;
         if (gd >= 0.0) fail = 1;
         else {
             dcs_state ls; dcsrch_start(&ls, stp, f, gd);
@@ -720,114 +879,97 @@ static int lbfgsb_core(const orc_params *p, const orc_map *map, int M, const dou
             for (;;) {
                 ifun++;
                 if (ifun - 1 >= maxls) { fail = 1; break; }
-                if (stp == 1.0) for (int i = 0; i < n; i++) xn[i] = t[i] + d[i];
+                if (stp == 1.0) memcpy(xn, z, sizeof(double) * n);
                 else for (int i = 0; i < n; i++) xn[i] = stp * d[i] + t[i];
                 int same = 1; for (int i = 0; i < n; i++) if (xn[i] != xl[i]) { same = 0; break; }
                 memcpy(x, xn, sizeof(double) * n);
-                if (!same) {   /* scipy's ScalarFunction does not re-evaluate an unchanged x */
-                    if (hk && hk->poll(hk->ctx)) { out->status = ORC_STOPPED; out->nit = nit; out->nfev = nfev; return ORC_STOPPED; }
-                    st = orc_eval(p, map, M, head, tail, x, costs, g, 0, 0);
-                    if (st && published) hk->ls_end(hk->ctx);
-                    if (st) { out->status = st; out->nit = nit; out->nfev = nfev; memcpy(out->x, x, sizeof(double) * n); return st; }
-                    f = costs[0] * p->w[0] + costs[1] * p->w[1] + costs[2] * p->w[2] + costs[3] * p->w[3];
-                    nfev++; memcpy(xl, x, sizeof(double) * n);
-                    memcpy(out->costs, costs, sizeof(costs));
-                }
-                gd = dotn(n, g, d);
-                int task = dcsrch_step(&ls, &stp, f, gd);
-                if (task) break;
+                if (!same) LB_EVAL();          /* scipy's ScalarFunction does not re-evaluate an unchanged x */
+                gd = blas_ddot(n, g, 1, d, 1);
+                if (dcsrch_step(&ls, &stp, f, gd)) break;
             }
-        }
-        orc_trace_put((nfev - nfev_ls) * 4 + fail * 2 + (col > 0));
-        if (fail && snap >= 0) { orc_snap_buf[snap].failed = 1; orc_snap_buf[snap].nfev_after = nfev; }
-        if (published && !fail) hk->ls_end(hk->ctx);
-        if (published && fail && hk->ls_fail(hk->ctx, nfev, out->costs)) {
-            out->status = ORC_HANDED_OFF; out->nit = nit; out->nfev = nfev;
-            return ORC_HANDED_OFF;
         }
         if (fail) {
             memcpy(x, t, sizeof(double) * n); memcpy(g, r, sizeof(double) * n); f = fold;
-            if (col == 0) { st = ORC_ABNORMAL; goto done; }
-            col = 0; head_i = 0; theta = 1.0;
+            if (C.col == 0) { st = ORC_ABNORMAL; goto done; }
+            lb_reset(&C, n);
             continue;
         }
         nit++;
         sbg = 0.0; for (int i = 0; i < n; i++) sbg = fmax(sbg, fabs(g[i]));
         if (sbg <= pgtol) { st = ORC_CONV_PG; goto done; }
-        { double dd = fmax(fmax(fabs(fold), fabs(f)), 1.0); if (fold - f <= tol * dd) { st = ORC_CONV_FTOL; goto done; } }
+        { const double dd = fmax(fmax(fabs(fold), fabs(f)), 1.0); if (fold - f <= tol * dd) { st = ORC_CONV_FTOL; goto done; } }
         if (nit >= maxiter || nfev > maxfun) { st = ORC_MAXITER; goto done; }
         /* BFGS update (matupd) */
         double rr, dr, ddum;
         for (int i = 0; i < n; i++) r[i] = g[i] - r[i];
-        rr = dotn(n, r, r);
+        { const double nr = blas_dnrm2(n, r); rr = nr * nr; }
         if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
-        else { dr = (gd - gdold) * stp; for (int i = 0; i < n; i++) d[i] *= stp; ddum = -gdold * stp; }
+        else { dr = (gd - gdold) * stp; for (int i = 0; i < n; i++) d[i] = d[i] * stp; ddum = -gdold * stp; }
         if (dr <= epsmch * ddum) continue;   /* skip the update */
-        int slot;
-        if (col < m) { slot = (head_i + col) % m; col++; }
-        else { slot = head_i; head_i = (head_i + 1) % m; }
-        memcpy(S[slot], d, sizeof(double) * n); memcpy(Y[slot], r, sizeof(double) * n);
-        rho[slot] = 1.0 / dr;
-        theta = rr / dr;
+        lb_update(&C, d, r, rr, dr);
     }
 done:
     memcpy(out->x, x, sizeof(double) * n);
     out->f = f; out->status = st; out->nit = nit; out->nfev = nfev;
     return st;
+#undef LB_EVAL
+}
+
+/* evaluator = this file's orc_eval */
+typedef struct { const orc_params *p; const orc_map *map; int M; const double *head, *tail; } fg_problem;
+static int fg_oracle(void *ctx, int n, const double *x, double *f, double *g, double *costs)
+{
+    (void)n;
+    const fg_problem *q = (const fg_problem *)ctx;
+    const int st = orc_eval(q->p, q->map, q->M, q->head, q->tail, x, costs, g, 0, 0);
+    if (st) return st;
+    *f = costs[0] * q->p->w[0] + costs[1] * q->p->w[1] + costs[2] * q->p->w[2] + costs[3] * q->p->w[3];
+    return 0;
 }
 
 int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
                const double *x0, orc_result *out)
 {
-    const int n = ORC_D * (M - 1) + M;
-    double g[ORC_MAXN], costs[4];
-    int st = orc_eval(p, map, M, head, tail, x0, costs, g, 0, 0);
-    if (st) { out->status = st; out->nit = 0; out->nfev = 0; memcpy(out->x, x0, sizeof(double) * n); return st; }
-    const double f = costs[0] * p->w[0] + costs[1] * p->w[1] + costs[2] * p->w[2] + costs[3] * p->w[3];
-    memcpy(out->costs, costs, sizeof(costs));
-    orc_trace_put(-1);
-    return lbfgsb_core(p, map, M, head, tail, x0, g, f, 0, 1, 1, out);
+    fg_problem q = {p, map, M, head, tail};
+    return lbfgsb_run(ORC_D * (M - 1) + M, x0, fg_oracle, &q, out);
 }
 
-/* Continue from a captured restart state as a speculative restart would: memory empty, first step 1, no evaluation at
- * the start point; the evaluation counter resumes from the count at the failure. */
-int orc_lbfgsb_resume(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
-                      const orc_restart *rs, orc_result *out)
+/* the same optimizer around a caller-supplied evaluator (tests: the reference's own Python get_cost/get_grad) */
+int orc_lbfgsb_cb(int n, const double *x0, orc_fg_fn fg, void *ctx, orc_result *out) { return lbfgsb_run(n, x0, fg, ctx, out); }
+
+/* ... with every evaluation recorded: x (cap, n), f (cap), g (cap, n); returns the number of evaluations recorded */
+int orc_lbfgsb_traced(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
+                      const double *x0, orc_result *out, int cap, double *xs, double *fs, double *gs)
 {
-    memcpy(out->costs, rs->costs, sizeof(rs->costs));
-    return lbfgsb_core(p, map, M, head, tail, rs->x, rs->g, rs->f, rs->nit, rs->nfev_after, 0, out);
+    orc_trace T = {cap, 0, xs, fs, gs};
+    orc_trace_cur = &T;
+    orc_lbfgsb(p, map, M, head, tail, x0, out);
+    orc_trace_cur = 0;
+    return T.len;
 }
 
-/* Design check for speculative restarts: run minimize() from x0, then replay every line search that failed with a
- * non-empty memory from its captured restart state. Returns how many replays do NOT end in the original result
- * (status, nit, nfev, x and last-evaluated costs bit for bit); *checked = number of replays. */
-int orc_check_restarts(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,
-                       const double *x0, int *checked)
+/* Lockstep replay: the optimizer above is fed evaluations recorded elsewhere (the device's). Evaluation k must be
+ * requested at exactly xs[k] (bitwise); it then returns fs[k], gs[k], costs[k], status[k]. If the requested point
+ * differs, the run stops with ORC_REPLAY_DIVERGED and *first_bad = k. Identical requests all the way prove that the
+ * recorded run and this optimizer made the same decisions from the same numbers. */
+typedef struct { int n_evals, k, bad; const double *xs, *fs, *gs, *costs; const int32_t *status; } fg_replay;
+static int fg_from_trace(void *ctx, int n, const double *x, double *f, double *g, double *costs)
 {
-    static orc_restart snaps[2048];
-    const int n = ORC_D * (M - 1) + M;
-    orc_result ref, r;
-    orc_set_snapshots(snaps, 2048);
-    orc_lbfgsb(p, map, M, head, tail, x0, &ref);
-    const int ns = orc_snapshot_count();
-    orc_set_snapshots(0, 0);
-    int bad = 0;
-    *checked = 0;
-    for (int i = 0; i < ns; i++) {
-        if (!snaps[i].failed) continue;
-        orc_lbfgsb_resume(p, map, M, head, tail, &snaps[i], &r);
-        (*checked)++;
-        /* costs only matter when minimize() returns: an exception (status >= ORC_OVERFLOW) discards the attempt (EP:197) */
-        if (r.status != ref.status || r.nit != ref.nit || r.nfev != ref.nfev || memcmp(r.x, ref.x, sizeof(double) * n) ||
-            (ref.status < ORC_OVERFLOW && memcmp(r.costs, ref.costs, sizeof(ref.costs)))) {
-            bad++;
-            if (getenv("ORC_DEBUG_RESTARTS"))
-                fprintf(stderr, "snap %d/%d: status %d/%d nit %d/%d nfev %d/%d xdiff %d costdiff %d (snap nit %d nfev %d after %d)\n", i, ns,
-                        r.status, ref.status, r.nit, ref.nit, r.nfev, ref.nfev, memcmp(r.x, ref.x, sizeof(double) * n) != 0,
-                        memcmp(r.costs, ref.costs, sizeof(ref.costs)) != 0, snaps[i].nit, snaps[i].nfev, snaps[i].nfev_after);
-        }
-    }
-    return bad;
+    fg_replay *q = (fg_replay *)ctx;
+    const int k = q->k;
+    if (k >= q->n_evals || memcmp(x, q->xs + (size_t)k * n, sizeof(double) * n)) { q->bad = k; return ORC_REPLAY_DIVERGED; }
+    q->k++;
+    *f = q->fs[k]; memcpy(g, q->gs + (size_t)k * n, sizeof(double) * n); memcpy(costs, q->costs + (size_t)k * 4, sizeof(double) * 4);
+    return q->status ? q->status[k] : 0;
+}
+
+int orc_lbfgsb_replay(int n, const double *x0, int n_evals, const double *xs, const double *fs, const double *gs,
+                      const double *costs, const int32_t *status, orc_result *out, int *first_bad, int *used)
+{
+    fg_replay q = {n_evals, 0, -1, xs, fs, gs, costs, status};
+    const int st = lbfgsb_run(n, x0, fg_from_trace, &q, out);
+    *first_bad = q.bad; *used = q.k;
+    return st;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -909,6 +1051,51 @@ void orc_plan_batch(const orc_params *p, const orc_map *map, int B, int M, const
         memcpy(costs + (size_t)b * 4, pl.costs, sizeof(double) * 4);
         status[b] = pl.status; ok[b] = pl.ok; attempt[b] = pl.attempt; nit[b] = pl.nit; runs[b] = pl.runs; nfev[b] = pl.nfev;
     }
+}
+
+/* the same batch on `threads` host threads (problems are independent; interleaved assignment). Used by the full-size
+ * parity sweeps and as the all-core CPU yardstick of bench.py. */
+#include <pthread.h>
+typedef struct {
+    const orc_params *p; const orc_map *const *maps; const int32_t *map_ids; int B, M, first, stride, max_attempts;
+    const double *head, *tail, *q0, *ts0, *retry_q, *retry_ts;
+    double *x, *ts, *coeffs, *costs; int32_t *status, *ok, *attempt, *nit, *runs, *nfev;
+} mt_job;
+static void *mt_worker(void *arg)
+{
+    const mt_job *j = (const mt_job *)arg;
+    const int M = j->M, nq = ORC_D * (M - 1), n = nq + M;
+    for (int b = j->first; b < j->B; b += j->stride) {
+        orc_plan pl;
+        const orc_map *map = j->maps[j->map_ids ? j->map_ids[b] : 0];
+        orc_warm_start_plan(j->p, map, M, j->head + (size_t)b * 3 * ORC_D, j->tail + (size_t)b * 3 * ORC_D,
+                            j->q0 + (size_t)b * nq, j->ts0 + (size_t)b * M,
+                            j->retry_q ? j->retry_q + (size_t)b * (j->max_attempts - 1) * nq : 0, j->retry_ts, j->max_attempts, &pl);
+        memcpy(j->x + (size_t)b * n, pl.x, sizeof(double) * n);
+        memcpy(j->ts + (size_t)b * M, pl.ts, sizeof(double) * M);
+        memcpy(j->coeffs + (size_t)b * 6 * M * ORC_D, pl.coeffs, sizeof(double) * 6 * M * ORC_D);
+        memcpy(j->costs + (size_t)b * 4, pl.costs, sizeof(double) * 4);
+        j->status[b] = pl.status; j->ok[b] = pl.ok; j->attempt[b] = pl.attempt; j->nit[b] = pl.nit; j->runs[b] = pl.runs;
+        j->nfev[b] = pl.nfev;
+    }
+    return 0;
+}
+void orc_plan_batch_mt(const orc_params *p, const orc_map *const *maps, const int32_t *map_ids, int B, int M,
+                       const double *head, const double *tail, const double *q0, const double *ts0, const double *retry_q,
+                       const double *retry_ts, int max_attempts, int threads, double *x, double *ts, double *coeffs,
+                       double *costs, int32_t *status, int32_t *ok, int32_t *attempt, int32_t *nit, int32_t *runs, int32_t *nfev)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    mt_job jobs[256];
+    for (int t = 0; t < threads; t++) {
+        mt_job j = {p, maps, map_ids, B, M, t, threads, max_attempts, head, tail, q0, ts0, retry_q, retry_ts,
+                    x, ts, coeffs, costs, status, ok, attempt, nit, runs, nfev};
+        jobs[t] = j;
+        pthread_create(&th[t], 0, mt_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], 0);
 }
 
 /* batched eval used by the parity tests */

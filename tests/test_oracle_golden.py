@@ -1,5 +1,7 @@
 """Pins the two CPU checkers (oracle/minco_ref.py, oracle/minco_oracle.c) to golden vectors that
 oracle/gen_golden.py produced by running the unmodified reference (EP/ESDF/TU, scipy L-BFGS-B)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -118,7 +120,7 @@ def _status_class(msg):
     return 4   # exception
 
 
-@pytest.mark.parametrize('name,min_match', [('plans_M3.npz', 0.95), ('plans_M10.npz', 0.9)])
+@pytest.mark.parametrize('name,min_match', [('plans_M3.npz', 0.97), ('plans_M10.npz', 0.95)])
 def test_plan_once_c_oracle(golden, name, min_match):
     """The restated L-BFGS-B (C) follows scipy's iterates: same termination class, nit, and final x
     to 1e-6 on all but the few line-search knife-edge problems (documented in DESIGN.md)."""
@@ -272,28 +274,45 @@ def test_astar_oracle_unreachable_target(golden):
     assert astar_ref.astar_plain(gm, [2.5, 2.5], [10.5, 6.5]) == path
 
 
-def test_restart_state_reproduces_the_continuation_after_a_failed_line_search():
-    """Design pin for speculative restarts: {x, g, f, nit, nfev at the failure} captured at the start of
-    a line search is all the optimizer needs to continue after that search fails -- replaying from it (empty memory,
-    first step 1, no evaluation at the start point) ends in the same status, counters, x and costs."""
-    import ctypes as C
-    from neo_planner_b200 import guesses
-    from neo_planner_b200.worlds import make_problems, make_world, YamlConfig
-    from oracle import c_oracle
-    cfg = YamlConfig(); M = 3
-    w = make_world(0)
-    head, tail = make_problems(w, 96, M=M)
-    q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
-    p = c_oracle.Params.from_config(cfg); m = c_oracle.OracleMap.from_world(w)
-    hp, tp = c_oracle.pad_state(head), c_oracle.pad_state(tail)
-    lib = c_oracle.lib()
-    replayed = 0
-    for b in range(96):
-        tau = -np.log((cfg.T_max - cfg.T_min) / (ts0[b] - cfg.T_min) - 1)
-        x0 = np.ascontiguousarray(np.concatenate((q0[b].reshape(-1), tau)))
-        chk = C.c_int(0)
-        bad = lib.orc_check_restarts(C.byref(p), C.byref(m.c), C.c_int(M), hp[b].ctypes.data_as(C.c_void_p),
-                                     tp[b].ctypes.data_as(C.c_void_p), x0.ctypes.data_as(C.c_void_p), C.byref(chk))
-        assert bad == 0, b
-        replayed += chk.value
-    assert replayed >= 20
+@pytest.mark.parametrize('M,count', [(3, 48), (10, 8)])
+def test_lbfgsb_restatement_bit_identical_to_scipy(M, count):
+    """scipy's L-BFGS-B (third party, not vendored by the reference) is restated in oracle/minco_oracle.c
+    operation by operation -- compact representation (formk / subsm), the BLAS kernels' summation orders, x87 dnrm2.
+    Driven by the SAME evaluator (oracle/minco_ref.py's get_cost/get_grad, bit-identical to the reference where the
+    fixtures were made) the restatement and scipy.optimize.minimize must end in the same x BIT FOR BIT with the same
+    iteration and evaluation counts. (The arithmetic restated is that of the OpenBLAS kernels scipy selects on AVX-512
+    hosts; on another kernel family the last bits of scipy itself move -- then the test reports instead of failing.)"""
+    import scipy.optimize as sopt
+    cfg = YamlConfig(); cfg.init_wpts_num = M - 1
+    w = make_world(2)
+    grid = minco_ref.GridMap(w.occ, w.H, w.W, w.res, w.ox, w.oy)
+    from neo_planner_b200.worlds import make_problems
+    head, tail = make_problems(w, count, M=M)
+    opt = minco_ref.RefOptimizer(cfg)
+    same = ran = 0
+    for k in range(count):
+        q0, ts0 = opt.straight_line_guess(head[k], tail[k])
+        opt.set_problem(grid, head[k], tail[k], q0, ts0)
+        x0 = np.concatenate((q0.reshape(-1), opt.T2tau(ts0)))
+        try:
+            res = sopt.minimize(opt.cost, x0, method='L-BFGS-B', jac=opt.grad, bounds=None, tol=1e-4,
+                                options={'maxcor': 10, 'maxfun': 15000, 'maxiter': 15000, 'maxls': 20})
+        except (OverflowError, ValueError, ZeroDivisionError):
+            x, nit, nfev, st = c_oracle.lbfgsb_cb(lambda x: (opt.cost(x), opt.grad(x)), x0)
+            assert st >= 4
+            continue
+        x, nit, nfev, st = c_oracle.lbfgsb_cb(lambda x: (opt.cost(x), opt.grad(x)), x0)
+        ran += 1
+        same += int(np.array_equal(x, res.x) and nit == res.nit and nfev == res.nfev)
+    print(f'M={M}: {same}/{ran} minimize() runs bit-identical to scipy')
+    import ctypes, glob, scipy
+    core = b'?'
+    for so in glob.glob(os.path.join(os.path.dirname(scipy.__file__), '..', 'scipy.libs', '*openblas*')):
+        try:
+            f = ctypes.CDLL(so).scipy_openblas_get_corename; f.restype = ctypes.c_char_p; core = f()
+        except Exception:
+            pass
+    if core in (b'SkylakeX', b'?'):
+        assert same == ran, (same, ran)
+    else:
+        pytest.skip(f'OpenBLAS kernel family {core!r}: scipy itself rounds differently here ({same}/{ran} identical)')
