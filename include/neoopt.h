@@ -22,6 +22,12 @@
  *   void*; NULL = the handle's own stream) without synchronising. A handle owns ONE set of scratch buffers
  *   (work-queue counter, per-attempt records): consecutive _dev launches on the same handle must be ordered on the
  *   same stream, and maps must not be re-uploaded while a launch is in flight. Use one handle per concurrent stream.
+ *   map_ids passed to host-pointer entry points are validated (every id must name a slot that holds a map, else
+ *   NEO_ERR_INVALID); for _dev entry points that is a precondition (the ids are in device memory).
+ *   Kernel selection: problems with M <= 4 pieces run one per warp below NEO_TILE_MIN_PROBLEMS (4096) problems per call
+ *   and 4 (M <= 3) or 2 (M = 4) per warp from there on; results of the two schedules differ in the last bits of the
+ *   sampled sums (different partial-sum order), never in the algorithm. The one development switch read from the
+ *   environment at neo_create, NEO_TILE = 8 | 16 | 32, pins the lanes per problem (A/B measurements, parity tests).
  */
 #ifndef NEOOPT_H
 #define NEOOPT_H
@@ -131,6 +137,16 @@ typedef struct {
 int neo_optimize(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
                  const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
                  int max_attempts, neo_result *out);
+
+/* neo_optimize plus a record of what the device evaluated (parity tests: the recorded sequence is replayed through the
+ * CPU checker's optimizer, tests/test_gpu_lockstep.py). Per task t = attempt * B + problem the first trace_cap
+ * evaluations: tr_x (A*B, cap, n) trial points, tr_f (A*B, cap), tr_g (A*B, cap, n), tr_costs (A*B, cap, 4),
+ * tr_status (A*B, cap) 0 or the NEO_ST_* the evaluation raised, tr_len (A*B) evaluations made (0: task never ran).
+ * Speculative retries that were cancelled leave a partial record. */
+int neo_optimize_trace(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
+                       const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
+                       int max_attempts, neo_result *out, int trace_cap, double *tr_x, double *tr_f, double *tr_g,
+                       double *tr_costs, int32_t *tr_status, int32_t *tr_len);
 
 /* Device-pointer variant: every pointer (inputs, retry_*, and all non-NULL members of *out) is a DEVICE
  * pointer; the launch is enqueued on `stream` and not synchronised. Inputs are in tau form because

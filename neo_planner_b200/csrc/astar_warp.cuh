@@ -21,7 +21,7 @@
 #include <math.h>
 #include <stdint.h>
 
-#include "minco_warp.cuh"
+#include "minco_tile.cuh"
 
 namespace neo {
 

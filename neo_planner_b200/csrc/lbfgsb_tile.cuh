@@ -1,0 +1,514 @@
+// lbfgsb_tile.cuh -- scipy.optimize.minimize(method='L-BFGS-B', bounds=None, tol=1e-4, maxcor=10, maxls=20) exactly as
+// the reference calls it (EP:213-225), one tile of TL lanes per problem, the whole optimizer state on chip: lane l < n
+// owns component l of x, g, d, z and of the saved iterate; the limited-memory matrices live in the tile's shared-memory
+// slice; scalar logic (More'-Thuente dcsrch/dcstep of MINPACK-2, as used by L-BFGS-B 3.0's lnsrlb) is executed
+// redundantly and identically by all lanes of the tile. No host round trips.
+//
+// scipy is a third-party dependency of the reference (not vendored; scipy 1.18.1 = C port of L-BFGS-B 3.0 over OpenBLAS).
+// What is restated here is its ARITHMETIC, operation by operation, for the unbounded case -- the same restatement as
+// oracle/minco_oracle.c (which is bit-identical to scipy when both are fed the same f and g; tests/test_oracle_golden.py):
+//   * direction by the compact representation: formk (assemble [Y'Y/theta + D, R_z'; R_z, 0], Cholesky of the (1,1)
+//     block, triangular solve, Cholesky of the (2,2) block) and subsm (two triangular solves), then d = (x + step) - x
+//     as two rounded operations, and x_new = z when the step length is exactly 1;
+//   * the summation orders and fused/unfused multiply-adds of the BLAS kernels behind ddot, dpotrf (potf2 + dgemv_t),
+//     dtrtrs (trsv for one right-hand side, the blocked trsm kernel for several), daxpy, and the x87 dnrm2 (x87_nrm2.h);
+//     scipy's own loops (formk's inner products, subsm) are unfused multiply + add;
+//   * ftol = gtol = 1e-4 (tol), factr = ftol/eps; stop if max|g| <= 1e-4 or (f_old-f) <= 1e-4*max(|f_old|,|f|,1);
+//     first step min(1/|d|, 1e10) on iteration 0, else 1; dcsrch(ftol=1e-3, gtol=0.9, xtol=0.1, stpmin=0, stpmax=1e10);
+//     CONVERGENCE and WARNING exits are both accepted; a 21st evaluation request fails the search;
+//   * on a failed search: restore x, f, g; if the memory is empty -> ABNORMAL, else drop the memory and retry;
+//     the pair (s, y) is stored unless s'y <= eps * (-g_old's);
+//   * scipy's ScalarFunction does not re-evaluate an x identical to the last evaluated one (nfev bookkeeping).
+// Every operation whose rounding matters is written with the __d*_rn / __fma_rn intrinsics, which the compiler never
+// contracts or reassociates; tests/test_gpu_lockstep.py replays the device's recorded (x, f, g) sequence through the
+// checker's optimizer and requires every requested point to be bit-identical.
+#pragma once
+#include "minco_tile.cuh"
+#include "x87_nrm2.h"
+
+namespace neo {
+
+// ---- exactly rounded, never contracted -----------------------------------------------------------------------------
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+struct Dcsrch {
+    bool brackt;
+    int stage;
+    double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax;
+};
+
+#define LS_FTOL 1e-3
+#define LS_GTOL 0.9
+#define LS_XTOL 0.1
+#define LS_STPMIN 0.0
+#define LS_STPMAX 1e10
+
+__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(a, fmax(b, c)); }
+
+// theta = 3 (fa - fb) / (sb - sa) + da + db  (every operation rounded on its own, as the host code does)
+__device__ __forceinline__ double cubic_theta(double fa, double fb, double sb, double sa, double da, double db)
+{
+    return xadd(xadd(xdiv(xmul(3.0, xsub(fa, fb)), xsub(sb, sa)), da), db);
+}
+// gamma = s * sqrt((theta/s)^2 - (da/s)(db/s)), optionally clamped at zero under the root
+__device__ __forceinline__ double cubic_gamma(double s, double theta, double da, double db, bool clamp)
+{
+    const double ts = xdiv(theta, s);
+    double rad = xsub(xmul(ts, ts), xmul(xdiv(da, s), xdiv(db, s)));
+    if (clamp) rad = fmax(0.0, rad);
+    return xmul(s, xsqrt(rad));
+}
+
+__device__ __noinline__ void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
+                                    double fp, double dp, bool &brackt, double stpmin, double stpmax)
+{
+    const double sgnd = xmul(dp, xdiv(dx, fabs(dx)));
+    double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+    if (fp > fx) {
+        theta = cubic_theta(fx, fp, stp, stx, dx, dp);
+        s = max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = cubic_gamma(s, theta, dx, dp, false);
+        if (stp < stx) gamma = -gamma;
+        p = xadd(xsub(gamma, dx), theta); q = xadd(xadd(xsub(gamma, dx), gamma), dp); r = xdiv(p, q);
+        stpc = xadd(stx, xmul(r, xsub(stp, stx)));
+        stpq = xadd(stx, xmul(xdiv(xdiv(dx, xadd(xdiv(xsub(fx, fp), xsub(stp, stx)), dx)), 2.0), xsub(stp, stx)));
+        if (fabs(xsub(stpc, stx)) < fabs(xsub(stpq, stx))) stpf = stpc; else stpf = xadd(stpc, xdiv(xsub(stpq, stpc), 2.0));
+        brackt = true;
+    } else if (sgnd < 0.0) {
+        theta = cubic_theta(fx, fp, stp, stx, dx, dp);
+        s = max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = cubic_gamma(s, theta, dx, dp, false);
+        if (stp > stx) gamma = -gamma;
+        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dx); r = xdiv(p, q);
+        stpc = xadd(stp, xmul(r, xsub(stx, stp)));
+        stpq = xadd(stp, xmul(xdiv(dp, xsub(dp, dx)), xsub(stx, stp)));
+        if (fabs(xsub(stpc, stp)) > fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
+        brackt = true;
+    } else if (fabs(dp) < fabs(dx)) {
+        theta = cubic_theta(fx, fp, stp, stx, dx, dp);
+        s = max3(fabs(theta), fabs(dx), fabs(dp));
+        gamma = cubic_gamma(s, theta, dx, dp, true);
+        if (stp > stx) gamma = -gamma;
+        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(gamma, xsub(dx, dp)), gamma); r = xdiv(p, q);
+        if (r < 0.0 && gamma != 0.0) stpc = xadd(stp, xmul(r, xsub(stx, stp)));
+        else if (stp > stx) stpc = stpmax;
+        else stpc = stpmin;
+        stpq = xadd(stp, xmul(xdiv(dp, xsub(dp, dx)), xsub(stx, stp)));
+        if (brackt) {
+            if (fabs(xsub(stpc, stp)) < fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
+            if (stp > stx) stpf = fmin(xadd(stp, xmul(0.66, xsub(sty, stp))), stpf);
+            else stpf = fmax(xadd(stp, xmul(0.66, xsub(sty, stp))), stpf);
+        } else {
+            if (fabs(xsub(stpc, stp)) > fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
+            stpf = fmin(stpmax, stpf); stpf = fmax(stpmin, stpf);
+        }
+    } else {
+        if (brackt) {
+            theta = cubic_theta(fp, fy, sty, stp, dy, dp);
+            s = max3(fabs(theta), fabs(dy), fabs(dp));
+            gamma = cubic_gamma(s, theta, dy, dp, false);
+            if (stp > sty) gamma = -gamma;
+            p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dy); r = xdiv(p, q);
+            stpc = xadd(stp, xmul(r, xsub(sty, stp)));
+            stpf = stpc;
+        } else if (stp > stx) stpf = stpmax;
+        else stpf = stpmin;
+    }
+    if (fp > fx) { sty = stp; fy = fp; dy = dp; }
+    else {
+        if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+        stx = stp; fx = fp; dx = dp;
+    }
+    stp = stpf;
+}
+
+__device__ __forceinline__ void dcsrch_start(Dcsrch &S, double stp, double f, double g)
+{
+    S.brackt = false; S.stage = 1; S.finit = f; S.ginit = g; S.gtest = xmul(LS_FTOL, g);
+    S.width = LS_STPMAX - LS_STPMIN; S.width1 = xdiv(S.width, 0.5);
+    S.stx = 0.0; S.fx = f; S.gx = g; S.sty = 0.0; S.fy = f; S.gy = g;
+    S.stmin = 0.0; S.stmax = xadd(stp, xmul(4.0, stp));
+}
+
+// 0 = evaluate at stp, 1 = CONVERGENCE, 2 = WARNING
+__device__ __forceinline__ int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
+{
+    const double ftest = xadd(S.finit, xmul(stp, S.gtest));
+    int task = 0;
+    if (S.stage == 1 && f <= ftest && g >= 0.0) S.stage = 2;
+    if (S.brackt && (stp <= S.stmin || stp >= S.stmax)) task = 2;
+    if (S.brackt && xsub(S.stmax, S.stmin) <= xmul(LS_XTOL, S.stmax)) task = 2;
+    if (stp == LS_STPMAX && f <= ftest && g <= S.gtest) task = 2;
+    if (stp == LS_STPMIN && (f > ftest || g >= S.gtest)) task = 2;
+    if (f <= ftest && fabs(g) <= xmul(LS_GTOL, -S.ginit)) task = 1;
+    if (task) return task;
+    {   // a modified function is used in stage 1 while the decrease is not yet sufficient
+        const bool mod = S.stage == 1 && f <= S.fx && f > ftest;
+        const double gt = mod ? S.gtest : 0.0;
+        const double fm = xsub(f, xmul(stp, gt)), gm = xsub(g, gt);
+        double fxm = xsub(S.fx, xmul(S.stx, gt)), fym = xsub(S.fy, xmul(S.sty, gt)), gxm = xsub(S.gx, gt), gym = xsub(S.gy, gt);
+        dcstep(S.stx, fxm, gxm, S.sty, fym, gym, stp, fm, gm, S.brackt, S.stmin, S.stmax);
+        S.fx = xadd(fxm, xmul(S.stx, gt)); S.fy = xadd(fym, xmul(S.sty, gt));
+        S.gx = xadd(gxm, gt); S.gy = xadd(gym, gt);
+    }
+    if (S.brackt) {
+        if (fabs(xsub(S.sty, S.stx)) >= xmul(0.66, S.width1)) stp = xadd(S.stx, xmul(0.5, xsub(S.sty, S.stx)));
+        S.width1 = S.width; S.width = fabs(xsub(S.sty, S.stx));
+    }
+    if (S.brackt) { S.stmin = fmin(S.stx, S.sty); S.stmax = fmax(S.stx, S.sty); }
+    else { S.stmin = xadd(stp, xmul(1.1, xsub(stp, S.stx))); S.stmax = xadd(stp, xmul(4.0, xsub(stp, S.stx))); }
+    stp = fmax(stp, LS_STPMIN); stp = fmin(stp, LS_STPMAX);
+    if ((S.brackt && (stp <= S.stmin || stp >= S.stmax)) || (S.brackt && xsub(S.stmax, S.stmin) <= xmul(LS_XTOL, S.stmax)))
+        stp = S.stx;
+    return 0;
+}
+
+// ---- BLAS kernels restated (see the header of this file and oracle/minco_oracle.c) ------------------------------------
+// ddot: n < 16 fused multiply-adds in index order; 16 <= n < 32: the first 16 products rounded, four lanes, fold, then fma
+__device__ __forceinline__ double blas_ddot(int n, const double *a, const double *b)
+{
+    double s = 0.0;
+    int i = 0;
+    if (n >= 16) {
+        double v[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+            v[l] = xadd(xadd(xadd(xmul(a[l], b[l]), xmul(a[4 + l], b[4 + l])), xmul(a[8 + l], b[8 + l])), xmul(a[12 + l], b[12 + l]));
+        s = xadd(xadd(v[0], v[2]), xadd(v[1], v[3]));
+        i = 16;
+    }
+    for (; i < n; i++) s = xfma(a[i], b[i], s);
+    return s;
+}
+// a loop written out in scipy's own C: multiply, then add
+__device__ __forceinline__ double loop_dot(int n, const double *a, const double *b)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s = xadd(s, xmul(a[i], b[i]));
+    return s;
+}
+
+// packed upper triangle: element (i, j), i <= j
+__device__ __forceinline__ int wn_col(int j) { return j * (j + 1) / 2; }
+
+// dpotrf (OpenBLAS potf2_U) on the n x n diagonal block starting at row/column o. false: not positive definite.
+template <int TL>
+__device__ __forceinline__ bool lb_potf2(const Tile<TL> &T, double *wn, int o, int n)
+{
+    for (int j = 0; j < n; j++) {
+        double *cj = wn + wn_col(o + j) + o;                         // cj[k] = element (o + k, o + j)
+        double ajj = xsub(cj[j], blas_ddot(j, cj, cj));
+        if (!(ajj > 0.0)) return false;                               // same value in every lane of the tile
+        ajj = xsqrt(ajj);
+        T.sync();
+        if (T.tl == 0) cj[j] = ajj;
+        if (j < n - 1) {
+            const int m1 = j & ~3, k3 = j - m1;
+            const double r = xdiv(1.0, ajj);
+            for (int i = j + 1 + T.tl; i < n; i += TL) {
+                double *ci = wn + wn_col(o + i) + o;                 // ci[k] = element (o + k, o + i)
+                double v = ci[j];
+                if (m1) {                                             // dgemv_t kernel: four rows at a time in four lanes
+                    double acc[4];
+#pragma unroll
+                    for (int l = 0; l < 4; l++) acc[l] = xmul(ci[l], cj[l]);
+                    if (m1 == 8) {
+#pragma unroll
+                        for (int l = 0; l < 4; l++) acc[l] = xadd(acc[l], xmul(ci[4 + l], cj[4 + l]));
+                    }
+                    v = xsub(v, xadd(xadd(acc[0], acc[2]), xadd(acc[1], acc[3])));
+                }
+                if (k3 == 1) v = xfma(ci[m1], -cj[m1], v);
+                else if (k3 == 2) v = xadd(v, xfma(ci[m1], -cj[m1], xmul(ci[m1 + 1], -cj[m1 + 1])));
+                else if (k3 == 3) v = xadd(v, xfma(ci[m1 + 2], -cj[m1 + 2], xfma(ci[m1], -cj[m1], xmul(ci[m1 + 1], -cj[m1 + 1]))));
+                ci[j] = xmul(v, r);
+            }
+        }
+        T.sync();
+    }
+    return true;
+}
+
+// Per-tile limited-memory state that is not in shared memory (identical in every lane of the tile)
+struct LbMem {
+    int col, head, iupdat;
+    double theta;
+};
+
+__device__ __forceinline__ int lb_slot(const LbMem &L, int k) { const int s = L.head + k; return s >= HIST ? s - HIST : s; }
+
+// matupd + the bookkeeping formk does for a new pair: s, y are the lane-owned components (tl < n)
+template <int TL>
+__device__ __forceinline__ void lb_update(const Tile<TL> &T, const TileMem &m, int n, LbMem &L, double s, double y, double rr, double dr)
+{
+    L.iupdat++;
+    if (L.iupdat <= HIST) L.col = L.iupdat;
+    else L.head = L.head + 1 == HIST ? 0 : L.head + 1;                // the oldest pair's slot is reused
+    const int col = L.col, slot = lb_slot(L, col - 1);
+    if (T.tl < n) { m.ws[slot * n + T.tl] = s; m.wy[slot * n + T.tl] = y; }
+    L.theta = xdiv(rr, dr);
+    if (T.tl == 0) m.dr[slot] = dr;
+    T.sync();
+    const double *ynew = m.wy + slot * n;
+    for (int e = T.tl; e < 2 * col; e += TL) {
+        if (e < col) {                                                 // row `col` of Y'Y
+            const int sj = lb_slot(L, e);
+            m.yr[slot * HIST + sj] = loop_dot(n, ynew, m.wy + sj * n);
+        } else {                                                       // column `col` of R_z
+            const int si = lb_slot(L, e - col);
+            const double v = loop_dot(n, m.ws + si * n, ynew);
+            if (si == slot) m.rzd[slot] = v; else m.yr[si * HIST + slot] = v;
+        }
+    }
+    T.sync();
+}
+
+// formk: assemble the middle matrix and factor it. false: a Cholesky factorisation failed (scipy drops the memory).
+template <int TL>
+__device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, const LbMem &L)
+{
+    const int col = L.col;
+    const double theta = L.theta;
+    double *wn = m.wn;
+    for (int iy = T.tl; iy < col; iy += TL) {
+        const int si = lb_slot(L, iy), is = col + iy;
+        double *c1 = wn + wn_col(iy), *c2 = wn + wn_col(is);
+        for (int jy = 0; jy <= iy; jy++) {
+            const int sj = lb_slot(L, jy);
+            double v = xdiv(m.yr[si * HIST + sj], theta);                               // Y'Y / theta
+            if (jy == iy) v = xadd(v, m.dr[si]);                                         // + D
+            c1[jy] = v;
+            c2[col + jy] = 0.0;                                                           // S'AA'S * theta (no active set)
+        }
+        for (int jy = 0; jy < iy; jy++) c2[jy] = -0.0;                                   // -L_a'
+        for (int jy = iy; jy < col; jy++) {
+            const int sj = lb_slot(L, jy);
+            c2[jy] = jy == iy ? m.rzd[si] : m.yr[si * HIST + sj];                        // R_z'
+        }
+    }
+    // NOTE the transposition: formk fills wn(jy, is) = R_z(iy, jy) for jy >= iy -- column `is`, rows jy: c2[jy] above.
+    T.sync();
+    if (!lb_potf2(T, wn, 0, col)) return false;
+    if (col == 1) {                                                    // one right-hand side: trsv, a true division
+        if (T.tl == 0) wn[wn_col(1)] = xdiv(wn[wn_col(1)], wn[0]);
+    } else {                                                           // blocked trsm kernel: 8, 4, 2, 1 rows
+        for (int c = col + T.tl; c < 2 * col; c += TL) {
+            double *b = wn + wn_col(c);
+            int kk = 0;
+            for (int bs = 8; bs > 0; bs >>= 1) {
+                if (!(col & bs)) continue;
+                if (kk > 0)
+                    for (int i = kk; i < kk + bs; i++) {
+                        const double *ui = wn + wn_col(i);
+                        double acc = 0.0;
+                        for (int k = 0; k < kk; k++) acc = xfma(ui[k], b[k], acc);
+                        b[i] = xsub(b[i], acc);
+                    }
+                for (int i = kk; i < kk + bs; i++) {
+                    b[i] = xmul(b[i], xdiv(1.0, wn[wn_col(i) + i]));
+                    for (int k = i + 1; k < kk + bs; k++) b[k] = xfma(-b[i], wn[wn_col(k) + i], b[k]);
+                }
+                kk += bs;
+            }
+        }
+    }
+    T.sync();
+    for (int js = col; js < 2 * col; js++) {
+        const double *cjs = wn + wn_col(js);
+        for (int is = col + T.tl; is <= js; is += TL)
+            wn[wn_col(js) + is] = xadd(wn[wn_col(js) + is], blas_ddot(col, wn + wn_col(is), cjs));
+    }
+    T.sync();
+    return lb_potf2(T, wn, col, col);
+}
+
+// subsm with r = -g: returns the lane-owned component of the subspace step
+template <int TL>
+__device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, int n, const LbMem &L, double g)
+{
+    const int col = L.col, m2 = 2 * col;
+    const double theta = L.theta;
+    double *wn = m.wn, *wv = m.wn + wn_col(LBW);
+    double d = -g;
+    if (T.tl < n) m.dv[T.tl] = d;
+    T.sync();
+    for (int e = T.tl; e < m2; e += TL)
+        wv[e] = e < col ? loop_dot(n, m.wy + lb_slot(L, e) * n, m.dv) : xmul(theta, loop_dot(n, m.ws + lb_slot(L, e - col) * n, m.dv));
+    T.sync();
+    // trsv, transposed: b_i = (b_i - ddot(i, u(0:i, i), b)) / u_ii. Every row's inner product is a chain of fused
+    // multiply-adds in index order, so all rows advance together as each b_k becomes final.
+    {
+        constexpr int RPL = (LBW + TL - 1) / TL;
+        double s[RPL];
+#pragma unroll
+        for (int q = 0; q < RPL; q++) s[q] = 0.0;
+        for (int k = 0; k < m2; k++) {
+            if ((k & (TL - 1)) == T.tl) {
+                double v = wv[k];
+                if (k > 0) {
+                    double sk = s[0];
+#pragma unroll
+                    for (int q = 1; q < RPL; q++) if (k / TL == q) sk = s[q];
+                    v = xsub(v, sk);
+                }
+                wv[k] = xdiv(v, wn[wn_col(k) + k]);
+            }
+            T.sync();
+            const double bk = wv[k];
+#pragma unroll
+            for (int q = 0; q < RPL; q++) {
+                const int r = T.tl + q * TL;
+                if (r > k && r < m2) {
+                    const double *ur = wn + wn_col(r);
+                    if (r < 16 || k >= 16) s[q] = xfma(ur[k], bk, s[q]);
+                    else if (k == 15) s[q] = blas_ddot(16, ur, wv);    // the kernel's 16-element prefix (four lanes, fold)
+                }
+            }
+        }
+    }
+    T.sync();
+    for (int i = T.tl; i < col; i += TL) wv[i] = -wv[i];
+    T.sync();
+    // trsv, not transposed: b_i /= u_ii, then b_k = fma(-b_i, u_ki, b_k)
+    for (int i = m2 - 1; i >= 0; i--) {
+        const double *ui = wn + wn_col(i);
+        if (T.tl == 0) wv[i] = xdiv(wv[i], ui[i]);
+        T.sync();
+        const double t = -wv[i];
+        for (int k = T.tl; k < i; k += TL) wv[k] = xfma(t, ui[k], wv[k]);
+        T.sync();
+    }
+    if (T.tl < n) {
+        for (int jy = 0; jy < col; jy++) {
+            const int sj = lb_slot(L, jy);
+            d = xadd(xadd(d, xdiv(xmul(m.wy[sj * n + T.tl], wv[jy]), theta)), xmul(m.ws[sj * n + T.tl], wv[col + jy]));
+        }
+        d = xmul(d, xdiv(1.0, theta));
+    }
+    T.sync();
+    return d;
+}
+
+// ---- the optimizer as a state machine around ONE evaluation site ------------------------------------------------------
+constexpr int ST_CANCELLED = 7;      // a speculative retry stopped because an earlier attempt was accepted (never reported)
+constexpr int ST_RUNNING = -1;
+
+struct OptState {
+    double x, g, d, t, r, z, xlast;          // lane-owned components
+    double f, fold, stp, gd, gdold;
+    Dcsrch ls;
+    LbMem L;
+    double costs[4];                         // at the last evaluated point (EP:233)
+    unsigned long long ns, nv, nc;
+    int nit, nfev, ifun, status;
+    bool first;
+};
+
+__device__ __forceinline__ void opt_begin(OptState &o, double x0l)
+{
+    o.x = x0l; o.g = 0.0; o.d = 0.0; o.t = 0.0; o.r = 0.0; o.z = 0.0; o.xlast = 0.0;
+    o.f = 0.0; o.fold = 0.0; o.stp = 0.0; o.gd = 0.0; o.gdold = 0.0;
+    o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0;
+    o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
+    o.ns = o.nv = o.nc = 0;
+    o.nit = 0; o.nfev = 0; o.ifun = 0; o.status = ST_RUNNING; o.first = true;
+}
+
+// true: x is bit-identical to the last evaluated point (no evaluation, scipy's ScalarFunction cache)
+template <int TL>
+__device__ __forceinline__ bool opt_same_point(const Tile<TL> &T, const OptState &o, int n)
+{
+    return !o.first && T.all(T.tl >= n || o.x == o.xlast);
+}
+
+// g . d with the BLAS kernel's summation order (both vectors go through shared memory so that every lane can add them)
+template <int TL>
+__device__ __forceinline__ double opt_gd(const Tile<TL> &T, const TileMem &m, int n, double g, double d)
+{
+    T.sync();
+    if (T.tl < n) { m.gv[T.tl] = g; m.dv[T.tl] = d; }
+    T.sync();
+    return blas_ddot(n, m.gv, m.dv);
+}
+
+// Called after every evaluation (or cache hit) with f, g in place: one step of plan_once's minimize() (EP:213-225).
+// Leaves the next trial point in o.x, or sets o.status (>= 0) when minimize() returns.
+// cancel_word/cancel_mask: when (*cancel_word & cancel_mask) becomes non-zero (an earlier attempt of the same problem
+// has been accepted, so this speculative attempt can never be the returned one) the run stops with ST_CANCELLED.
+template <int TL>
+__device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m, int n, OptState &o,
+                                            const unsigned *cancel_word, unsigned cancel_mask)
+{
+    const bool mine = T.tl < n;
+    const double pgtol = 1e-4, ftol = 1e-4, epsmch = 2.220446049250313e-16;
+    const double tol = (ftol / epsmch) * epsmch;
+    const int maxls = 20, maxiter = 15000, maxfun = 15000;
+    bool new_dir;
+    if (o.first) {
+        o.first = false;
+        if (T.dmax(mine ? fabs(o.g) : 0.0) <= pgtol) { o.status = 1; return; }
+        new_dir = true;
+    } else {
+        o.gd = opt_gd(T, m, n, o.g, o.d);
+        if (dcsrch_step(o.ls, o.stp, o.f, o.gd) == 0) new_dir = false;            // FG: another trial point
+        else {
+            // ---- the line search accepted the last evaluated point -------------------------------------------------
+            o.nit++;
+            if (cancel_mask) {
+                unsigned w = 0;
+                if (T.tl == 0) w = *reinterpret_cast<const volatile unsigned *>(cancel_word);
+                if (T.shfl(w, 0) & cancel_mask) { o.status = ST_CANCELLED; return; }
+            }
+            if (T.dmax(mine ? fabs(o.g) : 0.0) <= pgtol) { o.status = 1; return; }
+            if (xsub(o.fold, o.f) <= xmul(tol, max3(fabs(o.fold), fabs(o.f), 1.0))) { o.status = 0; return; }
+            if (o.nit >= maxiter || o.nfev > maxfun) { o.status = 3; return; }
+            const double y = xsub(o.g, o.r);                                       // matupd
+            T.sync();
+            if (mine) m.dv[T.tl] = y;
+            T.sync();
+            const double nr = x87_nrm2(n, m.dv);
+            const double rr = xmul(nr, nr);
+            double dr, ddum, s;
+            if (o.stp == 1.0) { dr = xsub(o.gd, o.gdold); ddum = -o.gdold; s = o.d; }
+            else { dr = xmul(xsub(o.gd, o.gdold), o.stp); s = xmul(o.d, o.stp); ddum = xmul(-o.gdold, o.stp); }
+            if (!(dr <= xmul(epsmch, ddum))) lb_update(T, m, n, o.L, s, y, rr, dr);
+            new_dir = true;
+        }
+    }
+    for (;;) {      // (re)start a line search; loops only when a failed search drops the memory
+        if (new_dir) {
+            // ---- direction: Cauchy point x - g with an empty memory (theta = 1), else the subspace step; d = z - x ---
+            if (o.L.col > 0 && !lb_factor(T, m, o.L)) { o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0; }
+            if (o.L.col == 0) o.z = xsub(o.x, o.g);
+            else o.z = xadd(o.x, lb_step(T, m, n, o.L, o.g));
+            o.d = mine ? xsub(o.z, o.x) : 0.0;
+            // ---- lnsrlb: set up the search -----------------------------------------------------------------------
+            T.sync();
+            if (mine) m.dv[T.tl] = o.d;
+            T.sync();
+            const double dnorm = x87_nrm2(n, m.dv);
+            o.stp = (o.nit == 0) ? fmin(xdiv(1.0, dnorm), LS_STPMAX) : 1.0;
+            o.t = o.x; o.r = o.g; o.fold = o.f;
+            o.gd = opt_gd(T, m, n, o.g, o.d);
+            o.gdold = o.gd;
+            o.ifun = 0;
+            if (o.gd >= 0.0) o.ifun = maxls + 1;                                // not a descent direction: fail
+            else dcsrch_start(o.ls, o.stp, o.f, o.gd);
+        }
+        o.ifun++;
+        if (o.ifun - 1 < maxls) break;                                          // evaluate the trial point
+        // ---- failed search: restore the iterate; ABNORMAL if the memory is already empty --------------------------
+        o.x = o.t; o.g = o.r; o.f = o.fold;
+        if (o.L.col == 0) { o.status = 2; return; }
+        o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0;
+        new_dir = true;
+    }
+    o.x = (o.stp == 1.0) ? o.z : xadd(xmul(o.stp, o.d), o.t);
+}
+
+}  // namespace neo

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "minco_warp.cuh"
+#include "minco_tile.cuh"
 
 namespace neo {
 

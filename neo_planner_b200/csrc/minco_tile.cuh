@@ -1,4 +1,4 @@
-// minco_warp.cuh -- one warp = one planning problem: fused get_cost + get_grad of the reference optimizer
+// minco_tile.cuh -- one TILE of TL lanes (8, 16 or 32; TL >= 2M and TL >= n) = one planning problem: fused get_cost + get_grad of the reference optimizer
 // (EP:539-585) in fp64 on sm_100a.
 //
 // The reference solves the dense 6M x 6M MINCO system A c = b (EP:261-336, numpy.linalg.solve) and its transpose
@@ -13,6 +13,8 @@
 // This is algebraically identical to the reference (verified to ~1e-13 against numpy in scratch prototypes and to
 // <= 1e-12 in tests/test_gpu_parity.py) and turns ~6M sequential pivots into M-1 sequential 2x2 blocks.
 //
+// A warp holds 32/TL tiles; every shuffle, vote and barrier below names only the tile's own lanes (Tile::mask), so the
+// tiles of a warp are independent problems that merely share an instruction stream.
 //   tau -> T (EP:477-483, double-double exp)                       lanes 0..M-1
 //   node blocks, right-hand sides                                   lanes 1..M-1 (one interior node each)
 //   block elimination / back substitution                           lanes 0,1 (one per dimension)
@@ -34,11 +36,13 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // Phase timestamps for the development latency probe (k_eval_ticks in neoopt.cu); compiled out everywhere else.
 #ifdef NEO_TICKS
-#define NEO_TICK(i) do { __syncwarp(); if (ticks) ticks[i] = clock64(); } while (0)
+#define NEO_TICK(i) do { T.sync(); if (ticks) ticks[i] = clock64(); } while (0)
 #else
 #define NEO_TICK(i) do { } while (0)
 #endif
 constexpr int HIST = 10;        // L-BFGS memory (maxcor, EP:220)
+constexpr int LBW = 2 * HIST;   // order of the middle matrix of the compact representation
+constexpr int WN_DOUBLES = LBW * (LBW + 1) / 2 + LBW + 2;    // packed upper triangle + the subspace vector wv
 
 struct DevParams {
     double v_max2, T_min, T_max, safe_dis, dt;
@@ -59,8 +63,32 @@ struct MapView {
     const unsigned char *blocked;   // astar_warp.cuh: has_collision at every node of the enlarged search grid (1 = blocked)
 };
 
-// Per-warp shared-memory slice (all doubles). n = 3M-2 decision variables.
-struct WarpMem {
+// The TL lanes that work on one problem.
+template <int TL>
+struct Tile {
+    int tl;            // lane within the tile
+    unsigned mask;     // the tile's lanes within the warp
+    int base;          // first lane of the tile
+    __device__ __forceinline__ explicit Tile(int lane)
+        : tl(lane & (TL - 1)), mask(TL == 32 ? FULL : (((1u << (TL & 31)) - 1u) << (lane & ~(TL - 1)))), base(lane & ~(TL - 1)) {}
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(mask, v, src, TL); }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, src, TL); }
+    __device__ __forceinline__ unsigned shfl(unsigned v, int src) const { return __shfl_sync(mask, v, src, TL); }
+    __device__ __forceinline__ bool all(bool p) const { return __all_sync(mask, p); }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p); }
+    __device__ __forceinline__ int rmax(int v) const { return __reduce_max_sync(mask, v); }
+    __device__ __forceinline__ unsigned radd(unsigned v) const { return __reduce_add_sync(mask, v); }
+    __device__ __forceinline__ double dmax(double v) const
+    {
+#pragma unroll
+        for (int o = TL / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, TL));
+        return v;
+    }
+};
+
+// Per-tile shared-memory slice (all doubles). n = 3M-2 decision variables.
+struct TileMem {
     double *ts;    // [M]
     double *ex;    // [M]      exp(-tau)
     double *iT;    // [M][5]   1/T, 1/T^2, ... 1/T^5
@@ -78,33 +106,46 @@ struct WarpMem {
     double *nsd;   // [M][2]   sample count of the piece (as double) and its reciprocal
     double *gout;  // [n]      gradient staging
     double *ht;    // [12]     head (3,2), tail (3,2)
-    double *S;     // [HIST][n]
-    double *Y;     // [HIST][n]
-    double *rho;   // [HIST]
-    double *al;    // [HIST]   two-loop recursion coefficients
-    double *red;   // [15 or 15*M][33] per-lane partial sums of the sample loop (padded rows)
-    double *lw;    // [M][2]   first lane and lane count of each piece (SAMPLE_ALL_PIECES)
     double *pc;    // [M][2]   per-piece feasibility / collision cost
+    // optimizer (lbfgsb_tile.cuh): the limited-memory pairs, oldest first, and the inner products formk keeps
+    double *ws;    // [HIST][n]  s pairs, ring: pair k lives in row (head + k) % HIST
+    double *wy;    // [HIST][n]  y pairs
+    double *yr;    // [HIST][HIST] by ring slots: [newer][older] = y_newer . y_older (formk's Y'Y), [older][newer] =
+                   //          s_older . y_newer (formk's R_z, the upper triangle of S'Y), [a][a] = y_a . y_a
+    double *rzd;   // [HIST]   s_a . y_a as formk computes it (its own inner product, not matupd's dr)
+    double *dr;    // [HIST]   diagonal of S'Y as matupd stores it ((gd - gdold) * stp), by ring slot
+    double *gv;    // [n]      g and d as vectors every lane can read (sequential inner products)
+    double *dv;    // [n]
+    // one region, two users: per-lane partial sums of the sample loop (evaluation) / the factored middle matrix (direction)
+    double *red;   // [15 or 15*M][TL+1] per-lane partial sums of the sample loop (padded rows)
+    double *wn;    // [LBW(LBW+1)/2] packed upper triangle, column j at j(j+1)/2; then wv [LBW]
+    double *lw;    // [M][2]   first lane and lane count of each piece (SAMPLE_ALL_PIECES)
     double *nsprev; // [M]     sample counts the cached lane assignment was computed for (-1: none)
     double *asg;   // [32]     cached lane assignment: piece + 16 * width + 1024 * rank
 };
 
 // staging rows of the sample loop's partial sums: one block of 15 rows per piece when all pieces are parked before the
 // owners add them (by-piece schedule, latency-optimised), one block otherwise (see eval_fg)
-__host__ __device__ inline int red_doubles(int M, bool one_block) { return (M > 4 || one_block) ? 15 * 33 : 15 * 33 * M; }
+__host__ __device__ inline int red_doubles(int M, int TL, bool one_block) { return (M > 4 || one_block) ? 15 * (TL + 1) : 15 * (TL + 1) * M; }
+__host__ __device__ inline int shared_region_doubles(int M, int TL, bool one_block)
+{
+    const int r = red_doubles(M, TL, one_block);
+    return r > WN_DOUBLES ? r : WN_DOUBLES;
+}
 
-__host__ __device__ inline int warp_mem_doubles(int M, bool one_block = false)
+__host__ __device__ inline int tile_mem_doubles(int M, int TL = 32, bool one_block = false)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * HIST * n + 2 * HIST + red_doubles(M, one_block) + 4 * M + M + 32;
+              2 * M + 2 * M + n + 12 + 2 * M + 2 * HIST * n + HIST * HIST + 2 * HIST + 2 * n +
+              shared_region_doubles(M, TL, one_block) + (M > 4 ? 2 * M + M + 32 : 0);
     return (tot + 1) & ~1;
 }
 
-__device__ inline WarpMem carve(double *base, int M, bool one_block = false)
+__device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block = false)
 {
     const int n = 3 * M - 2, M1 = M + 1;
-    WarpMem m;
+    TileMem m;
     m.ts = base; base += M;
     m.ex = base; base += M;
     m.iT = base; base += 5 * M;
@@ -122,38 +163,27 @@ __device__ inline WarpMem carve(double *base, int M, bool one_block = false)
     m.nsd = base; base += 2 * M;
     m.gout = base; base += n;
     m.ht = base; base += 12;
-    m.S = base; base += HIST * n;
-    m.Y = base; base += HIST * n;
-    m.rho = base; base += HIST;
-    m.al = base; base += HIST;
-    m.red = base; base += red_doubles(M, one_block);       // per-lane partial sums: one block or one per piece
-    m.lw = base; base += 2 * M;
     m.pc = base; base += 2 * M;
-    m.nsprev = base; base += M;
-    m.asg = base;
+    m.ws = base; base += HIST * n;
+    m.wy = base; base += HIST * n;
+    m.yr = base; base += HIST * HIST;
+    m.rzd = base; base += HIST;
+    m.dr = base; base += HIST;
+    m.gv = base; base += n;
+    m.dv = base; base += n;
+    m.red = base; m.wn = base; base += shared_region_doubles(M, TL, one_block);
+    m.lw = base; m.nsprev = base + 2 * M; m.asg = base + 3 * M;      // only carved for M > 4 (see tile_mem_doubles)
     return m;
 }
 
-__device__ __forceinline__ double warp_sum(double v)
+// Called when a tile starts on a new problem: head/tail states into shared memory, cached lane assignment dropped.
+template <int TL>
+__device__ __forceinline__ void begin_problem(const Tile<TL> &T, const TileMem &m, int M, const double *head, const double *tail)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-
-__device__ __forceinline__ double warp_max(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
-// Called when a warp starts on a new problem: head/tail states into shared memory, cached lane assignment dropped.
-__device__ __forceinline__ void begin_problem(const WarpMem &m, int M, int lane, const double *head, const double *tail)
-{
+    const int lane = T.tl;
     if (lane < 6) { m.ht[lane] = head[lane]; m.ht[6 + lane] = tail[lane]; }
-    if (lane < M) { m.nsprev[lane] = -1.0; m.pc[2 * lane] = 0.0; m.pc[2 * lane + 1] = 0.0; }
-    __syncwarp();
+    if (lane < M) { if (M > 4) m.nsprev[lane] = -1.0; m.pc[2 * lane] = 0.0; m.pc[2 * lane + 1] = 0.0; }
+    T.sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -161,8 +191,10 @@ __device__ __forceinline__ void begin_problem(const WarpMem &m, int M, int lane,
 // ---------------------------------------------------------------------------------------------------------
 
 // Writes node positions / boundary (v,a) from the decision vector and the head/tail states.
-__device__ __forceinline__ void load_nodes(const WarpMem &m, int M, int lane, double xl)
+template <int TL>
+__device__ __forceinline__ void load_nodes(const Tile<TL> &T, const TileMem &m, int M, double xl)
 {
+    const int lane = T.tl;
     const int nq = 2 * (M - 1);
     if (lane < nq) {   // x = [q_x(0..M-2), q_y(0..M-2), tau] (EP:211): node i+1, dim d
         const int d = lane / (M - 1), i = lane - d * (M - 1);
@@ -174,15 +206,17 @@ __device__ __forceinline__ void load_nodes(const WarpMem &m, int M, int lane, do
         m.U[lane] = m.ht[2 + lane]; m.U[2 + lane] = m.ht[4 + lane];
         m.U[4 * M + lane] = m.ht[8 + lane]; m.U[4 * M + 2 + lane] = m.ht[10 + lane];
     }
-    __syncwarp();
+    T.sync();
 }
 
 // Block-tridiagonal system of the interior nodes (jerk + snap continuity) and its block elimination. Every lane runs
 // the M-1 sequential 2x2 steps for dimension d = lane & 1 with the blocks, right-hand sides and the running inverse in
 // registers (the blocks depend on 1/T^k only; nothing on the dependent chain goes through shared memory). Leaves
 // L, D'^-1, U per node in m.blk (reused by the adjoint) and the node (v, a) in m.U.
-__device__ __forceinline__ void solve_nodes(const WarpMem &m, int M, int lane)
+template <int TL>
+__device__ __forceinline__ void solve_nodes(const Tile<TL> &T, const TileMem &m, int M)
 {
+    const int lane = T.tl;
     const int d = lane & 1;
     const double *__restrict__ iT = m.iT;
     const double *__restrict__ P = m.P;
@@ -221,7 +255,7 @@ __device__ __forceinline__ void solve_nodes(const WarpMem &m, int M, int lane)
         u00 = n00; u01 = n01; u10 = n10; u11 = n11; p0 = r0; p1 = r1;
         a = b; a2 = b2; a3 = b3; a4 = b4; pm = pc; pc = pn;
     }
-    __syncwarp();
+    T.sync();
     {
         double v = tv, ac = ta;
         for (int j = M - 1; j >= 1; j--) {
@@ -232,12 +266,14 @@ __device__ __forceinline__ void solve_nodes(const WarpMem &m, int M, int lane)
             if (lane < 2) { m.U[4 * j + d] = v; m.U[4 * j + 2 + d] = ac; }
         }
     }
-    __syncwarp();
+    T.sync();
 }
 
 // Quintic coefficients of piece i, dimension d from its boundary states (closed-form Hermite inverse).
-__device__ __forceinline__ void hermite_coeffs(const WarpMem &m, int M, int lane)
+template <int TL>
+__device__ __forceinline__ void hermite_coeffs(const Tile<TL> &T, const TileMem &m, int M)
 {
+    const int lane = T.tl;
     if (lane < 2 * M) {
         const int i = lane >> 1, d = lane & 1;
         const double T = m.ts[i], T2 = T * T;
@@ -251,7 +287,7 @@ __device__ __forceinline__ void hermite_coeffs(const WarpMem &m, int M, int lane
         c[8] = (-30.0 * dl + (14.0 * ve + 16.0 * vs) * T + (3.0 * as - 2.0 * ae) * T2) * (0.5 * a4);
         c[10] = (12.0 * dl - 6.0 * (ve + vs) * T - (as - ae) * T2) * (0.5 * a5);
     }
-    __syncwarp();
+    T.sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -349,11 +385,13 @@ __device__ __forceinline__ void sample_point(const DevParams &P, const MapView &
 }
 
 // tau -> T for all pieces; returns 0 or the status the reference's exception maps to. Also fills 1/T^k.
-__device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem &m, int M, int lane, double xl,
+template <int TL>
+__device__ __forceinline__ int times_from_tau(const Tile<TL> &T, const DevParams &P, const TileMem &m, int M, double xl,
                                               double &e_out)
 {
+    const int lane = T.tl;
     const int nq = 2 * (M - 1);
-    const double tau = __shfl_sync(FULL, xl, (nq + lane) & 31);
+    const double tau = T.shfl(xl, (nq + lane) & (TL - 1));
     int bad = 0;
     double e = 0.0;
     if (lane < M) {
@@ -374,51 +412,53 @@ __device__ __forceinline__ int times_from_tau(const DevParams &P, const WarpMem 
         m.pc[2 * lane] = 0.0; m.pc[2 * lane + 1] = 0.0;        // a piece without samples contributes no penalty
     }
     e_out = e;
-    bad = __reduce_max_sync(FULL, bad);
-    __syncwarp();
+    bad = T.rmax(bad);
+    T.sync();
     return bad;
 }
 
-template <int MODE>
-__device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, const WarpMem &m, int M, int lane,
+template <int MODE, int TL>
+__device__ __forceinline__ void eval_fg(const Tile<TL> &T, const DevParams &P, const MapView &map, const TileMem &m, int M,
                                         double xl, bool want_grad, EvalOut &out, long long *ticks = nullptr)
 {
+    static_assert(MODE != SAMPLE_ALL_PIECES || TL == 32, "the all-pieces schedule assigns the 32 lanes of a warp");
+    const int lane = T.tl;
     NEO_TICK(0);
     const int nq = 2 * (M - 1);
     out.status = 0; out.ns = out.nv = out.nc = 0;
     out.g = 0.0;
 
     double e;
-    int bad = times_from_tau(P, m, M, lane, xl, e);
+    int bad = times_from_tau(T, P, m, M, xl, e);
     if (bad) { out.status = bad; out.f = 0.0; out.costs[0] = out.costs[1] = out.costs[2] = out.costs[3] = 0.0; return; }
 
     // ---- coefficients (EP:261-336) ----------------------------------------------------------------
     NEO_TICK(1);
-    load_nodes(m, M, lane, xl);
-    solve_nodes(m, M, lane);
+    load_nodes(T, m, M, xl);
+    solve_nodes(T, m, M);
     NEO_TICK(2);
-    hermite_coeffs(m, M, lane);
+    hermite_coeffs(T, m, M);
     NEO_TICK(3);
 
     // ---- energy + time (EP:345-390): lane (piece i, dim d) -------------------------------------------
     if (lane < 2 * M) {
         const int i = lane >> 1, d = lane & 1;
-        const double T = m.ts[i], T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
+        const double Ti = m.ts[i], T2 = Ti * Ti, T3 = T2 * Ti, T4 = T3 * Ti, T5 = T4 * Ti;
         const double *ci = m.c + 12 * i + d;
         const double c3 = ci[6], c4 = ci[8], c5 = ci[10];
-        const double r3 = 36.0 * T * c3 + 72.0 * T2 * c4 + 120.0 * T3 * c5;     // rows of beta3_mat @ c
+        const double r3 = 36.0 * Ti * c3 + 72.0 * T2 * c4 + 120.0 * T3 * c5;     // rows of beta3_mat @ c
         const double r4 = 72.0 * T2 * c3 + 192.0 * T3 * c4 + 360.0 * T4 * c5;
         const double r5 = 120.0 * T3 * c3 + 360.0 * T4 * c4 + 720.0 * T5 * c5;
         m.e0[lane] = c3 * r3 + c4 * r4 + c5 * r5;
         double *g = m.gC + 12 * i + d;
         g[0] = 0.0; g[2] = 0.0; g[4] = 0.0;
         g[6] = (P.w0 * 2.0) * r3; g[8] = (P.w0 * 2.0) * r4; g[10] = (P.w0 * 2.0) * r5;
-        const double jend = 6.0 * c3 + 24.0 * T * c4 + 60.0 * T2 * c5;         // jerk at the piece end
+        const double jend = 6.0 * c3 + 24.0 * Ti * c4 + 60.0 * T2 * c5;         // jerk at the piece end
         const double je2 = P.w0 * (jend * jend);
-        const double other = __shfl_xor_sync(0xffffffffu >> (32 - 2 * M), je2, 1);
+        const double other = __shfl_xor_sync(((1u << (2 * M)) - 1u) << T.base, je2, 1, TL);
         if (d == 0) m.gT[i] = (je2 + other) + P.w1;
     }
-    __syncwarp();
+    T.sync();
     double costs0 = 0.0, costs1 = 0.0;
     for (int i = 0; i < M; i++) {          // sequential, like the reference's loops / np.sum
         costs0 += m.e0[2 * i] + m.e0[2 * i + 1];
@@ -428,10 +468,10 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
     NEO_TICK(4);
     // ---- sampled penalties (EP:392-466) -----------------------------------------------------------------
     double costs2 = 0.0, costs3 = 0.0;
-    if (MODE == SAMPLE_BY_PIECE || MODE == SAMPLE_BY_PIECE_STAGED) {
+    if constexpr (MODE == SAMPLE_BY_PIECE || MODE == SAMPLE_BY_PIECE_STAGED) {
         // few pieces (M <= 4): one piece at a time, lanes over its samples; every lane parks its 15 partial sums of the
-        // piece in shared memory (row = (piece, slot), padded to 33 so that the owners below read conflict-free).
-        // Owner (piece, slot) adds the 32 per-lane partial sums in lane order (four interleaved chains): uniform trip
+        // piece in shared memory (row = (piece, slot), padded to TL + 1 so that the owners below read conflict-free).
+        // Owner (piece, slot) adds the TL per-lane partial sums in lane order (four interleaved chains): uniform trip
         // counts, no shuffles, deterministic. SAMPLE_BY_PIECE parks all pieces first and lets 15 M owners work at once
         // (shortest dependent chain); SAMPLE_BY_PIECE_STAGED re-uses one block and reduces after every piece (same
         // additions in the same order, a third of the shared memory).
@@ -447,39 +487,39 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
             double acc[16];
 #pragma unroll
             for (int s2 = 0; s2 < 16; s2++) acc[s2] = 0.0;
-            for (int j = lane; j < ns; j += 32) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
-            double *row = m.red + (STAGED ? 0 : 15 * i) * 33 + lane;
+            for (int j = lane; j < ns; j += TL) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
+            double *row = m.red + (STAGED ? 0 : 15 * i) * (TL + 1) + lane;
 #pragma unroll
-            for (int s2 = 0; s2 < 15; s2++) row[s2 * 33] = acc[s2];
+            for (int s2 = 0; s2 < 15; s2++) row[s2 * (TL + 1)] = acc[s2];
             if (STAGED) {
-                __syncwarp();
-                if (lane < 15) {
-                    const double *p = m.red + lane * 33;
+                T.sync();
+                for (int o = lane; o < 15; o += TL) {
+                    const double *p = m.red + o * (TL + 1);
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
+                    for (int k = 0; k < TL; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
                     const double tot = (a0 + a1) + (a2 + a3);
-                    if (lane < 12) m.gC[12 * i + lane] += tot;
-                    else if (lane == 12) m.gT[i] += tot;
-                    else m.pc[2 * i + (lane - 13)] = tot;
+                    if (o < 12) m.gC[12 * i + o] += tot;
+                    else if (o == 12) m.gT[i] += tot;
+                    else m.pc[2 * i + (o - 13)] = tot;
                 }
-                __syncwarp();
+                T.sync();
             }
         }
         if (!STAGED) {
-            __syncwarp();
-            for (int o = lane; o < 15 * M; o += 32) {
-                const double *p = m.red + o * 33;
+            T.sync();
+            for (int o = lane; o < 15 * M; o += TL) {
+                const double *p = m.red + o * (TL + 1);
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
+                for (int k = 0; k < TL; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
                 const double tot = (a0 + a1) + (a2 + a3);
                 const int i = o / 15, s2 = o - 15 * i;
                 if (s2 < 12) m.gC[12 * i + s2] += tot;
                 else if (s2 == 12) m.gT[i] += tot;
                 else m.pc[2 * i + (s2 - 13)] = tot;
             }
-            __syncwarp();
+            T.sync();
         }
         for (int i = 0; i < M; i++) { costs2 += m.pc[2 * i]; costs3 += m.pc[2 * i + 1]; }
     } else {
@@ -513,7 +553,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
                 my_rank = lane - plo; my_width = phi - plo;
             }
             m.asg[lane] = (double)(my_piece + 16 * my_width + 1024 * my_rank);
-            __syncwarp();
+            T.sync();
         } else {
             const int v = (int)m.asg[lane];
             my_piece = v & 15; my_width = (v >> 4) & 63; my_rank = v >> 10;
@@ -533,7 +573,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
 #pragma unroll
             for (int s2 = 0; s2 < 15; s2++) m.red[s2 * 33 + lane] = acc[s2];
         }
-        __syncwarp();
+        T.sync();
         {   // owner (piece i, slot s): slot = lane % 16, two pieces per pass, four interleaved chains in fixed order
             const int s2 = lane & 15;
             for (int i = lane >> 4; i < M; i += 2) {
@@ -552,18 +592,18 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
                 else if (s2 < 15) m.pc[2 * i + (s2 - 13)] = tot;
             }
         }
-        __syncwarp();
+        T.sync();
         for (int i = 0; i < M; i++) { costs2 += m.pc[2 * i]; costs3 += m.pc[2 * i + 1]; }
     }
-    bad = __reduce_max_sync(FULL, bad);
-    out.ns = __reduce_add_sync(FULL, out.ns);
-    out.nv = __reduce_add_sync(FULL, out.nv);
-    out.nc = __reduce_add_sync(FULL, out.nc);
+    bad = T.rmax(bad);
+    out.ns = T.radd(out.ns);
+    out.nv = T.radd(out.nv);
+    out.nc = T.radd(out.nc);
     out.costs[0] = costs0; out.costs[1] = costs1; out.costs[2] = costs2; out.costs[3] = costs3;
     out.f = costs0 * P.w0 + costs1 * P.w1 + costs2 * P.w2 + costs3 * P.w3;
     if (bad) { out.status = bad; return; }
     if (!want_grad) return;
-    __syncwarp();
+    T.sync();
 
     NEO_TICK(5);
     // ---- adjoint (EP:494-537) ------------------------------------------------------------------------
@@ -582,7 +622,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         h[8] = -4.0 * a2 * g3 + 7.0 * a3 * g4 - 3.0 * a4 * g5;
         h[10] = 0.5 * a * g3 - a2 * g4 + 0.5 * a3 * g5;
     }
-    __syncwarp();
+    T.sync();
     NEO_TICK(6);
     // eta_j = dW/d(v_j, a_j) at the interior nodes, then K^T lam = eta by block elimination (lanes 0/1 per dim);
     // the Schur complements of K^T are the transposes of those of K, so D'^-1 from the forward solve is reused.
@@ -602,7 +642,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
             y1 = B[5] * e0 + B[7] * e1;
             if (lane < 2) { m.r[4 * j + d] = y0; m.r[4 * j + 2 + d] = y1; }
         }
-        __syncwarp();
+        T.sync();
         double l0 = 0.0, l1 = 0.0;
         for (int j = M - 1; j >= 1; j--) {
             const double *B = m.blk + 12 * j;
@@ -618,7 +658,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         }
         if (lane < 2) { m.lam[d] = 0.0; m.lam[2 + d] = 0.0; m.lam[4 * M + d] = 0.0; m.lam[4 * M + 2 + d] = 0.0; }
     }
-    __syncwarp();
+    T.sync();
     NEO_TICK(7);
     // G rows of interior node j (reference rows 6(j-1)+3 .. 6(j-1)+8), lane (j, d): grad_q and the T-gradient inputs
     if (lane >= 2 && lane < 2 * M) {
@@ -639,7 +679,7 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         G[0] = Gq + Gp; G[2] = Gv; G[4] = Ga; G[6] = lJ; G[8] = lS;
         m.gout[d * (M - 1) + (j - 1)] = Gq;              // grad_q[d][j-1] = G[6(j-1)+3][d] (EP:506-508)
     }
-    __syncwarp();
+    T.sync();
     NEO_TICK(8);
     // grad_T (EP:511-533): piece i < M-1 uses T_i; the last piece re-uses the loop variable T = ts[M-2]
     if (lane < M) {
@@ -672,9 +712,9 @@ __device__ __forceinline__ void eval_fg(const DevParams &P, const MapView &map, 
         const double gTi = m.gT[i] - tr;
         m.gout[nq + i] = gTi * (P.T_max - P.T_min) * e / ((1.0 + e) * (1.0 + e));      // EP:485-492
     }
-    __syncwarp();
+    T.sync();
     out.g = (lane < nq + M) ? m.gout[lane] : 0.0;
-    __syncwarp();
+    T.sync();
     NEO_TICK(9);
 }
 

@@ -13,9 +13,9 @@
 
 #include "../../include/neoopt.h"
 #include "astar_warp.cuh"
-#include "lbfgs_warp.cuh"
+#include "lbfgsb_tile.cuh"
 #include "map_kernels.cuh"
-#include "minco_warp.cuh"
+#include "minco_tile.cuh"
 
 using namespace neo;
 
@@ -23,16 +23,15 @@ using namespace neo;
 // kernels
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
-#ifndef NEO_MIN_CTAS
-#define NEO_MIN_CTAS 2
+#ifndef NEO_TILE_MIN_PROBLEMS
+#define NEO_TILE_MIN_PROBLEMS 4096   // batch size from which short trajectories (M <= 4) run several problems per warp
 #endif
 #ifndef NEO_PACKED_MIN_PER_SM
 #define NEO_PACKED_MIN_PER_SM 324    // problems x pieces per SM from which the 3-CTAs-per-SM instantiation is launched
-#endif                               // (measured break-even: M = 3 near 16 k problems, M = 10 near 4 k, scripts/gpu_ab_min_ctas.py)
+#endif                               // (measured break-even for one problem per warp: M = 10 near 4 k problems)
 
 struct OptArgs {
     int B, M, max_attempts;
-    int lockstep;                // 1: warps of a CTA synchronise before every evaluation (large batches)
     const double *x0;            // (B,n) tau form
     const int32_t *x0_status;    // (B) or null: NEO_ST_DOMAIN where map_T2tau failed on the host
     const double *head, *tail;   // (B,3,2)
@@ -42,7 +41,7 @@ struct OptArgs {
     int retry_status;            // NEO_ST_DOMAIN if retry_ts is outside (T_min, T_max)
     const MapView *maps;
     unsigned int *counter;       // work queue head
-    // per-task records (task = attempt * B + problem), written by the warp that ran the attempt
+    // per-task records (task = attempt * B + problem), written by the tile that ran the attempt
     double *t_x;                 // (A*B, n)
     double *t_costs;             // (A*B, 4)
     int32_t *t_info;             // (A*B, 4): status, nit, nfev, completed (minimize() returned)
@@ -51,10 +50,10 @@ struct OptArgs {
     double *x, *ts, *coeffs, *costs;
     int32_t *status, *ok, *attempt, *nit, *runs, *nfev;
     long long *work;
-    // speculative restarts (experimental, SHADOW instantiations only; appended so that the other fields keep their offsets)
-    ShadowSlot *slots;           // (A*B), zeroed per launch
-    unsigned int *n_resolved;    // problems resolved so far (the idle phase ends when it reaches B)
-    unsigned int *req_bits;      // ceil(A*B / 32) words: tasks with a restart request out (discovery only)
+    // optional evaluation trace (neo_optimize_trace; all null otherwise): per task the first trace_cap evaluations
+    int trace_cap;
+    double *tr_x, *tr_f, *tr_g, *tr_costs;   // (A*B, cap, n), (A*B, cap), (A*B, cap, n), (A*B, cap, 4)
+    int32_t *tr_status, *tr_len;             // (A*B, cap), (A*B)
 };
 
 // A problem is resolved once its lowest accepted attempt has all earlier attempts finished, or all attempts finished.
@@ -65,134 +64,130 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
     return done == (1u << A) - 1u;
 }
 
-// Persistent warps pull TASKS = (attempt, problem) from a global queue in attempt-major order and run one
-// plan_once (EP:205-237) per task entirely on chip. warm_start_plan (EP:186-203) semantics are kept exactly -- the
-// returned attempt is the lowest-index accepted one and counters are summed over attempts 0..that one -- but a retry
-// whose predecessor is still running on another warp is started SPECULATIVELY on an otherwise idle warp (its inputs,
-// straight line + host-drawn noise, do not depend on the predecessor). A speculative attempt is skipped or cancelled
-// as soon as an earlier attempt of its problem is accepted. With many problems per SM the queue reaches the retries
-// only when first attempts are finished, so speculation costs nothing; with few problems it halves the tail.
-// The warp whose completion resolves a problem assembles its outputs (final coefficients included).
+// Persistent TILES (TL lanes; 32 / TL per warp) pull TASKS = (attempt, problem) from a global queue in attempt-major
+// order and run one plan_once (EP:205-237) per task entirely on chip. warm_start_plan (EP:186-203) semantics are kept
+// exactly -- the returned attempt is the lowest-index accepted one and counters are summed over attempts 0..that one --
+// but a retry whose predecessor is still running elsewhere is started SPECULATIVELY on an otherwise idle tile (its
+// inputs, straight line + host-drawn noise, do not depend on the predecessor). A speculative attempt is skipped or
+// cancelled as soon as an earlier attempt of its problem is accepted. The tile whose completion resolves a problem
+// assembles its outputs (final coefficients included).
+// The loop below is the WARP's loop: every round each running tile evaluates f, g at its trial point (one shared
+// evaluation site, so the tiles of a warp walk through the evaluator together) and then advances its own optimizer
+// (lbfgsb_tile.cuh: opt_advance); a tile whose task ends takes the next one in the same round.
+// TL = 32: one problem per warp -- lowest latency per evaluation (few problems per SM, or M >= 5 where n > 16).
+// TL = 8 / 16: 4 / 2 problems per warp for short trajectories (n <= TL, 2M <= TL) -- with n = 7 decision variables and
+//   ~20 samples per piece a whole warp is mostly idle lanes; tiles cut the issue slots per evaluation ~2x.
 // MC: the number of pieces as a compile-time constant (loops over pieces/nodes unroll, lane maps fold).
-// MINB: CTAs per SM the register allocation is sized for. 2 (231 registers) is fastest when the launch is bound by the
-// longest chain of evaluations (few problems per SM); 3 (168 registers, 12 warps per SM) gives more throughput once
-// every SM has a queue of problems (launch_optimize picks by batch size; the arithmetic is the same).
-// SHADOW (experimental, NEO_SHADOW=1, small launches only): warps that find the queue empty serve restart requests of
-// running tasks (lbfgs_warp.cuh, protocol checked on the CPU in oracle/shadow_sim.c) until every problem is resolved.
-template <int MODE, int MC, int MINB, bool SHADOW = false>
+// MINB: CTAs per SM the register allocation is sized for.
+template <int MODE, int MC, int TL, int MINB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Tile<TL> T(lane);
+    constexpr int TPW = 32 / TL;
     const int M = MC > 0 ? MC : a.M, n = 3 * M - 2, nq = 2 * (M - 1), N = 6 * M, A = a.max_attempts;
     constexpr bool ONE_BLOCK = MODE == SAMPLE_BY_PIECE_STAGED;
-    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M, ONE_BLOCK), M, ONE_BLOCK);
+    const TileMem m = carve(smem + (size_t)(warp * TPW + lane / TL) * tile_mem_doubles(M, TL, ONE_BLOCK), M, TL, ONE_BLOCK);
     const unsigned total = (unsigned)A * (unsigned)a.B;
+    const bool mine = T.tl < n;
+    OptState o;
+    opt_begin(o, 0.0);
+    bool running = false, retired = false;
+    unsigned tid = 0, lower_ok = 0;
+    int at = 0;
+    size_t b = 0;
+    MapView map = a.maps[0];
+    unsigned long long t_start = 0;
     for (;;) {
-        unsigned int tid = 0;
-        if (lane == 0) tid = atomicAdd(a.counter, 1u);
-        tid = __shfl_sync(FULL, tid, 0);
-        bool as_claimant = false;
-        unsigned claimed_epoch = 0;
-        if (tid >= total) {
-            if constexpr (SHADOW) {
-                // idle phase: look for a restart request (lanes scan the request bitmap), claim it with a CAS on its slot
-                const unsigned nwords = (total + 31u) / 32u;
-                unsigned rot = (blockIdx.x * WARPS_PER_CTA + warp) % nwords;
-                for (;;) {
-                    if (*reinterpret_cast<volatile unsigned *>(a.n_resolved) >= (unsigned)a.B) break;
-                    for (unsigned w0 = 0; w0 < nwords && !as_claimant; w0 += 32) {
-                        const unsigned wi = (w0 + lane + rot) % nwords;
-                        const unsigned word = w0 + lane < nwords ? *reinterpret_cast<volatile unsigned *>(a.req_bits + wi) : 0u;
-                        const unsigned want = __ballot_sync(FULL, word != 0u);
-                        if (!want) continue;
-                        const int src = __ffs(want) - 1;
-                        const unsigned w_sel = __shfl_sync(FULL, wi, src), bits_sel = __shfl_sync(FULL, word, src);
-                        const unsigned t_sel = w_sel * 32u + (unsigned)(__ffs(bits_sel) - 1);
-                        if (t_sel >= total) continue;
-                        unsigned c_sel = 0, got = 0;
-                        if (lane == 0) {
-                            c_sel = sl_load(a.slots + t_sel);
-                            if ((c_sel & 3u) == SL_REQUESTED)
-                                got = atomicCAS(&a.slots[t_sel].ctl, c_sel, (c_sel & ~3u) | SL_CLAIMED) == c_sel;
-                            atomicAnd(a.req_bits + w_sel, ~(1u << (t_sel & 31u)));      // taken, or stale: either way not pending
-                        }
-                        c_sel = __shfl_sync(FULL, c_sel, 0); got = __shfl_sync(FULL, got, 0);
-                        if (got) { tid = t_sel; claimed_epoch = c_sel >> 2; as_claimant = true; }
+        if (__all_sync(FULL, retired)) break;
+        bool ended = false, report = false;      // this tile's task ended in this round / it has a record to write
+        if (!running && !retired) {
+            unsigned t0 = 0;
+            if (T.tl == 0) t0 = atomicAdd(a.counter, 1u);
+            tid = T.shfl(t0, 0);
+            if (tid >= total) retired = true;
+            else {
+                at = (int)(tid / (unsigned)a.B);
+                b = tid - (unsigned)at * (unsigned)a.B;
+                lower_ok = ((1u << at) - 1u) << 8;
+                unsigned seen = 0;
+                if (T.tl == 0) seen = *reinterpret_cast<volatile unsigned *>(a.p_state + b);
+                seen = T.shfl(seen, 0);
+                ended = true;
+                if (!(seen & lower_ok)) {         // else: an earlier attempt was already accepted, nothing to run
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+                    begin_problem(T, m, M, a.head + b * 6, a.tail + b * 6);
+                    map = a.maps[a.map_ids ? a.map_ids[b] : 0];
+                    double x0l = 0.0;
+                    int st0 = 0;
+                    if (at == 0) {
+                        if (mine) x0l = a.x0[b * n + T.tl];
+                        st0 = a.x0_status ? a.x0_status[b] : 0;
+                    } else {
+                        if (T.tl < nq) x0l = a.retry_q[(b * (A - 1) + (at - 1)) * nq + T.tl];
+                        else if (mine) x0l = a.retry_tau[T.tl - nq];
+                        st0 = a.retry_status;
                     }
-                    if (as_claimant) break;
-                    rot = (rot + 1u) % nwords;
-                    __nanosleep(1500);          // ~1,000 idle warps polling 640 B each: keep the L2 traffic in the 100s of GB/s
+                    opt_begin(o, x0l);
+                    report = true;
+                    if (st0) { o.status = st0; o.x = 0.0; }       // map_T2tau raised (EP:209)
+                    else { running = true; ended = false; }
                 }
-                if (!as_claimant) break;
-            } else {
-                if (a.lockstep) while (!__syncthreads_and(1)) { }      // keep meeting the busy warps until all are idle
-                break;
             }
         }
-        const int at = (int)(tid / (unsigned)a.B);
-        const size_t b = tid - (unsigned)at * (unsigned)a.B;
-        const unsigned lower_ok = ((1u << at) - 1u) << 8;
+        if (running) {
+            if (!opt_same_point(T, o, n)) {
+                // ---- the evaluation site: f, g at x --------------------------------------------------------------
+                EvalOut ev;
+                eval_fg<MODE, TL>(T, P, map, m, M, o.x, true, ev);
+                o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
+                if (a.tr_x && o.nfev < a.trace_cap) {
+                    const size_t k = (size_t)tid * a.trace_cap + o.nfev;
+                    if (mine) { a.tr_x[k * n + T.tl] = o.x; a.tr_g[k * n + T.tl] = ev.status ? 0.0 : ev.g; }
+                    if (T.tl < 4) a.tr_costs[k * 4 + T.tl] = ev.costs[T.tl];
+                    if (T.tl == 0) { a.tr_f[k] = ev.f; a.tr_status[k] = ev.status; a.tr_len[tid] = o.nfev + 1; }
+                }
+                if (ev.status) { o.status = ev.status; running = false; ended = true; report = true; }
+                else {
+                    o.f = ev.f; o.g = mine ? ev.g : 0.0; o.nfev++; o.xlast = o.x;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) o.costs[k] = ev.costs[k];
+                }
+            }
+            if (running) {
+                opt_advance(T, m, n, o, a.p_state + b, lower_ok);
+                if (o.status != ST_RUNNING) { running = false; ended = true; report = true; }
+            }
+        }
+        if (!ended) continue;
+
+        // ---- the task ended: record it, mark it in the problem's state word -------------------------------------
         unsigned bits = 1u << at;
-        const unsigned seen = *reinterpret_cast<volatile unsigned *>(a.p_state + b);
-        if (!(seen & lower_ok)) {
-            unsigned long long t_start;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-            begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
-            const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-            double x0l = 0.0;
-            int st0 = 0;
-            if (at == 0) {
-                if (lane < n) x0l = a.x0[b * n + lane];
-                st0 = a.x0_status ? a.x0_status[b] : 0;
-            } else {
-                if (lane < nq) x0l = a.retry_q[(b * (A - 1) + (at - 1)) * nq + lane];
-                else if (lane < n) x0l = a.retry_tau[lane - nq];
-                st0 = a.retry_status;
+        if (report && o.status != ST_CANCELLED) {
+            const bool completed = o.status < NEO_ST_OVERFLOW;             // minimize() returned (EP:213-233)
+            const bool accepted = completed && !(o.costs[3] * P.w3 > P.collision_cost_tol);   // EP:235-237
+            if (mine) a.t_x[(size_t)tid * n + T.tl] = o.x;
+            if (T.tl < 4) a.t_costs[(size_t)tid * 4 + T.tl] = o.costs[T.tl];
+            if (T.tl == 0) {
+                a.t_info[(size_t)tid * 4 + 0] = o.status; a.t_info[(size_t)tid * 4 + 1] = o.nit;
+                a.t_info[(size_t)tid * 4 + 2] = o.nfev; a.t_info[(size_t)tid * 4 + 3] = completed ? 1 : 0;
+                unsigned long long t_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+                a.t_work[(size_t)tid * 4 + 0] = (long long)o.ns; a.t_work[(size_t)tid * 4 + 1] = (long long)o.nv;
+                a.t_work[(size_t)tid * 4 + 2] = (long long)o.nc; a.t_work[(size_t)tid * 4 + 3] = (long long)(t_end - t_start);
             }
-            OptOut o;
-            o.status = st0; o.nit = 0; o.nfev = 0; o.ns = o.nv = o.nc = 0; o.x = 0.0;
-            o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
-            ShadowCtx sc;
-            if constexpr (SHADOW) {
-                sc.slot = a.slots + tid; sc.epoch = claimed_epoch; sc.owner = !as_claimant; sc.published = false;
-                sc.req_word = a.req_bits + (tid >> 5); sc.req_bit = 1u << (tid & 31u);
-                sc.t_start = t_start; sc.nanos_base = 0;
-                if (as_claimant) st0 = 0;
-            }
-            if (!st0) lbfgsb_warp<MODE, SHADOW>(P, map, m, M, lane, x0l, o, a.p_state + b, lower_ok, a.lockstep != 0, SHADOW ? &sc : nullptr);   // else map_T2tau raised (EP:209)
-            if constexpr (SHADOW) {
-                // a retired owner or an unneeded claimant reports nothing: the task's current owner will
-                if (o.status == ST_HANDED_OFF || o.status == ST_SUPERSEDED) continue;
-                t_start -= sc.nanos_base;               // time earlier owners of this task spent on it
-            }
-            if (o.status != ST_CANCELLED) {
-                const bool completed = o.status < NEO_ST_OVERFLOW;             // minimize() returned (EP:213-233)
-                const bool accepted = completed && !(o.costs[3] * P.w3 > P.collision_cost_tol);   // EP:235-237
-                if (lane < n) a.t_x[(size_t)tid * n + lane] = o.x;
-                if (lane < 4) a.t_costs[(size_t)tid * 4 + lane] = o.costs[lane];
-                if (lane == 0) {
-                    a.t_info[(size_t)tid * 4 + 0] = o.status; a.t_info[(size_t)tid * 4 + 1] = o.nit;
-                    a.t_info[(size_t)tid * 4 + 2] = o.nfev; a.t_info[(size_t)tid * 4 + 3] = completed ? 1 : 0;
-                    unsigned long long t_end;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-                    a.t_work[(size_t)tid * 4 + 0] = (long long)o.ns; a.t_work[(size_t)tid * 4 + 1] = (long long)o.nv;
-                    a.t_work[(size_t)tid * 4 + 2] = (long long)o.nc; a.t_work[(size_t)tid * 4 + 3] = (long long)(t_end - t_start);
-                }
-                if (accepted) bits |= 1u << (8 + at);
-                __threadfence();
-            }
-        } else if constexpr (SHADOW) {
-            if (as_claimant) continue;                  // claimed a task that is no longer needed: nothing to report
+            if (accepted) bits |= 1u << (8 + at);
+            __threadfence();
         }
-        __syncwarp();
+        T.sync();
         unsigned old = 0;
-        if (lane == 0) old = atomicOr(a.p_state + b, bits);
-        old = __shfl_sync(FULL, old, 0);
+        if (T.tl == 0) old = atomicOr(a.p_state + b, bits);
+        old = T.shfl(old, 0);
         const unsigned now = old | bits;
         if (!resolved(now, A) || resolved(old, A)) continue;
 
-        // ---- this warp resolved problem b: assemble warm_start_plan's outputs ---------------------------------
+        // ---- this tile resolved problem b: assemble warm_start_plan's outputs ---------------------------------
         __threadfence();
         const unsigned okm = (now >> 8) & 0xffu;
         const int last = okm ? __ffs(okm) - 1 : A - 1;      // returned attempt (EP:196-203)
@@ -209,33 +204,29 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
         }
         if (src >= 0) {      // final (int_wpts, ts) -> ts, coefficients (EP:226-229, TU:182)
             const size_t t = (size_t)src * a.B + b;
-            const double xf = lane < n ? __ldcg(a.t_x + t * n + lane) : 0.0;
-            begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
+            const double xf = mine ? __ldcg(a.t_x + t * n + T.tl) : 0.0;
+            begin_problem(T, m, M, a.head + b * 6, a.tail + b * 6);
             double e_unused;
-            times_from_tau(P, m, M, lane, xf, e_unused);
-            load_nodes(m, M, lane, xf);
-            solve_nodes(m, M, lane);
-            hermite_coeffs(m, M, lane);
-            if (lane < n) a.x[b * n + lane] = xf;
-            if (lane < M) a.ts[b * M + lane] = m.ts[lane];
-            for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = m.c[i];
-            if (lane < 4) a.costs[b * 4 + lane] = __ldcg(a.t_costs + t * 4 + lane);
+            times_from_tau(T, P, m, M, xf, e_unused);
+            load_nodes(T, m, M, xf);
+            solve_nodes(T, m, M);
+            hermite_coeffs(T, m, M);
+            if (mine) a.x[b * n + T.tl] = xf;
+            if (T.tl < M) a.ts[b * M + T.tl] = m.ts[T.tl];
+            for (int i = T.tl; i < 2 * N; i += TL) a.coeffs[b * 2 * N + i] = m.c[i];
+            if (T.tl < 4) a.costs[b * 4 + T.tl] = __ldcg(a.t_costs + t * 4 + T.tl);
         } else {
-            if (lane < n) a.x[b * n + lane] = 0.0;
-            if (lane < M) a.ts[b * M + lane] = 0.0;
-            for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = 0.0;
-            if (lane < 4) a.costs[b * 4 + lane] = 0.0;
+            if (mine) a.x[b * n + T.tl] = 0.0;
+            if (T.tl < M) a.ts[b * M + T.tl] = 0.0;
+            for (int i = T.tl; i < 2 * N; i += TL) a.coeffs[b * 2 * N + i] = 0.0;
+            if (T.tl < 4) a.costs[b * 4 + T.tl] = 0.0;
         }
-        if (lane == 0) {
+        if (T.tl == 0) {
             a.status[b] = status; a.ok[b] = okm ? 1 : 0; a.attempt[b] = last; a.nit[b] = nit; a.runs[b] = runs;
             a.nfev[b] = nfev;
             if (a.work) { a.work[b * 4] = ns; a.work[b * 4 + 1] = nv; a.work[b * 4 + 2] = nc; a.work[b * 4 + 3] = nanos; }
         }
-        __syncwarp();
-        if constexpr (SHADOW) {
-            __threadfence();
-            if (lane == 0) atomicAdd(a.n_resolved, 1u);
-        }
+        T.sync();
     }
 }
 
@@ -248,25 +239,29 @@ struct EvalArgs {
     int32_t *status;
 };
 
-template <int MODE, int MC>
+// get_cost + get_grad (EP:539-585) fused, one tile per problem
+template <int MODE, int MC, int TL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, const EvalArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Tile<TL> T(lane);
+    constexpr int TPW = 32 / TL, TPC = WARPS_PER_CTA * TPW;
     const int M = MC > 0 ? MC : a.M, n = 3 * M - 2, N = 6 * M;
-    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
-    for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)a.B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
-        begin_problem(m, M, lane, a.head + b * 6, a.tail + b * 6);
+    const int tile = warp * TPW + lane / TL;
+    const TileMem m = carve(smem + (size_t)tile * tile_mem_doubles(M, TL), M, TL);
+    for (size_t b = (size_t)blockIdx.x * TPC + tile; b < (size_t)a.B; b += (size_t)gridDim.x * TPC) {
+        begin_problem(T, m, M, a.head + b * 6, a.tail + b * 6);
         const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-        const double xl = lane < n ? a.x[b * n + lane] : 0.0;
+        const double xl = T.tl < n ? a.x[b * n + T.tl] : 0.0;
         EvalOut ev;
-        eval_fg<MODE>(P, map, m, M, lane, xl, true, ev);
-        if (lane < n) a.grad[b * n + lane] = ev.status ? 0.0 : ev.g;
-        if (lane < 4) a.costs[b * 4 + lane] = ev.costs[lane];
-        if (lane == 0) a.status[b] = ev.status;
-        if (a.coeffs) for (int i = lane; i < 2 * N; i += 32) a.coeffs[b * 2 * N + i] = ev.status == NEO_ST_OVERFLOW ? 0.0 : m.c[i];
-        if (a.ts && lane < M) a.ts[b * M + lane] = m.ts[lane];
-        __syncwarp();
+        eval_fg<MODE, TL>(T, P, map, m, M, xl, true, ev);
+        if (T.tl < n) a.grad[b * n + T.tl] = ev.status ? 0.0 : ev.g;
+        if (T.tl < 4) a.costs[b * 4 + T.tl] = ev.costs[T.tl];
+        if (T.tl == 0) a.status[b] = ev.status;
+        if (a.coeffs) for (int i = T.tl; i < 2 * N; i += TL) a.coeffs[b * 2 * N + i] = ev.status == NEO_ST_OVERFLOW ? 0.0 : m.c[i];
+        if (a.ts && T.tl < M) a.ts[b * M + T.tl] = m.ts[T.tl];
+        T.sync();
     }
 }
 
@@ -276,22 +271,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_coeffs(int B, int M, con
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Tile<32> T(lane);
     const int nq = 2 * (M - 1), N = 6 * M;
-    const WarpMem m = carve(smem + (size_t)warp * warp_mem_doubles(M), M);
+    const TileMem m = carve(smem + (size_t)warp * tile_mem_doubles(M), M);
     for (size_t b = (size_t)blockIdx.x * WARPS_PER_CTA + warp; b < (size_t)B; b += (size_t)gridDim.x * WARPS_PER_CTA) {
-        begin_problem(m, M, lane, head + b * 6, tail + b * 6);
+        begin_problem(T, m, M, head + b * 6, tail + b * 6);
         if (lane < M) {
-            const double T = ts[b * M + lane];
-            m.ts[lane] = T;
-            const double a = 1.0 / T, a2 = a * a;
+            const double Tt = ts[b * M + lane];
+            m.ts[lane] = Tt;
+            const double a = 1.0 / Tt, a2 = a * a;
             double *it = m.iT + 5 * lane;
             it[0] = a; it[1] = a2; it[2] = a2 * a; it[3] = a2 * a2; it[4] = a2 * a2 * a;
         }
         __syncwarp();
         const double xl = lane < nq ? q[b * nq + lane] : 0.0;
-        load_nodes(m, M, lane, xl);
-        solve_nodes(m, M, lane);
-        hermite_coeffs(m, M, lane);
+        load_nodes(T, m, M, xl);
+        solve_nodes(T, m, M);
+        hermite_coeffs(T, m, M);
         for (int i = lane; i < 2 * N; i += 32) coeffs[b * 2 * N + i] = m.c[i];
         __syncwarp();
     }
@@ -301,14 +297,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_coeffs(int B, int M, con
 __global__ void k_sample(int B, int M, const double *__restrict__ coeffs, const double *__restrict__ ts, double hz,
                          int max_samples, double *__restrict__ states, int32_t *__restrict__ count)
 {
-    const int b = blockIdx.y;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const double *T = ts + (size_t)b * M;
     double total = 0.0;
     for (int i = 0; i < M; i++) total += T[i];                    // Python sum(self.ts)
     const double step = 1.0 / hz;
     const int cnt = (int)ceil(total / step);                      // len(np.arange(0, total, 1/hz))
     if (blockIdx.x == 0 && threadIdx.x == 0) count[b] = cnt;
-    if (!states) return;
+    if (!states) continue;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt && k < max_samples; k += gridDim.x * blockDim.x) {
         const double t = (double)k * step;
         int piece = 0;
@@ -327,6 +323,7 @@ __global__ void k_sample(int B, int M, const double *__restrict__ coeffs, const 
             o[2 + d] = c1 + c2 * (2.0 * s) + c3 * (3.0 * s2) + c4 * (4.0 * s3) + c5 * (5.0 * s4);
             o[4 + d] = c2 * 2.0 + c3 * (6.0 * s) + c4 * (12.0 * s2) + c5 * (20.0 * s3);
         }
+    }
     }
 }
 
@@ -385,10 +382,8 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
-    int shadow = 0;                  // EXPERIMENTAL (env NEO_SHADOW = 1): speculative restarts in small M = 3 launches
-    int staged = -1;                 // development switch (env NEO_STAGED = 0 | 1; default -1: by shared-memory fit)
-    int min_ctas = 0;                // development switch (env NEO_MIN_CTAS_FORCE = 2 | 3): overrides the choice by batch size
-    int lockstep = 0;                // development switch (env NEO_LOCKSTEP at neo_create): CTA-level lockstep, see k_optimize
+    int tile = 0;                    // development switch (env NEO_TILE = 8 | 16 | 32 at neo_create; 0: by batch size):
+                                     // lanes per problem for M <= 4, see launch_optimize / include/neoopt.h
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     char name[128] = {0};
 };
@@ -474,10 +469,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     }
     neo_handle *h = new neo_handle();
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps);
-    if (const char *e = getenv("NEO_LOCKSTEP")) h->lockstep = atoi(e) != 0;
-    if (const char *e = getenv("NEO_MIN_CTAS_FORCE")) h->min_ctas = atoi(e);
-    if (const char *e = getenv("NEO_STAGED")) h->staged = atoi(e) != 0 ? 1 : 0;
-    if (const char *e = getenv("NEO_SHADOW")) h->shadow = atoi(e) != 0;
+    if (const char *e = getenv("NEO_TILE")) { const int t = atoi(e); h->tile = (t == 8 || t == 16 || t == 32) ? t : 0; }
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
     bool good = cudaSetDevice(device) == cudaSuccess &&
@@ -746,15 +738,30 @@ static int check_problem(neo_handle *h, int B, int M)
     return NEO_OK;
 }
 
-static size_t smem_bytes(int M, bool one_block = false)
+// host-pointer entry points: every map id must name a slot that holds a map (device-pointer entry points document it
+// as a precondition: the ids live in device memory)
+static int check_map_ids(neo_handle *h, int B, const int32_t *map_ids, const char *who)
 {
-    return sizeof(double) * (size_t)warp_mem_doubles(M, one_block) * WARPS_PER_CTA;
+    if (!map_ids) {
+        if (!h->slots[0].cells) { h->err = std::string(who) + ": map_ids is NULL and slot 0 holds no map"; return NEO_ERR_INVALID; }
+        return NEO_OK;
+    }
+    for (int i = 0; i < B; i++)
+        if (map_ids[i] < 0 || map_ids[i] >= (int)h->slots.size() || !h->slots[map_ids[i]].cells) {
+            h->err = std::string(who) + ": map id " + std::to_string(map_ids[i]) + " (problem " + std::to_string(i) + ") refers to an empty slot";
+            return NEO_ERR_INVALID;
+        }
+    return NEO_OK;
+}
+
+static size_t smem_bytes(int M, int TL = 32, bool one_block = false)
+{
+    return sizeof(double) * (size_t)tile_mem_doubles(M, TL, one_block) * WARPS_PER_CTA * (32 / TL);
 }
 
 template <typename K>
-static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm, bool one_block = false)
+static int prep_kernel(neo_handle *h, K kernel, size_t smem, int *ctas_per_sm)
 {
-    const size_t smem = smem_bytes(M, one_block);
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, WARPS_PER_CTA * 32, smem));
@@ -763,39 +770,45 @@ static int prep_kernel(neo_handle *h, K kernel, int M, int *ctas_per_sm, bool on
     return NEO_OK;
 }
 
+// lanes per problem: M >= 5 needs the warp (n > 16); short trajectories share a warp once the batch is large enough to
+// fill the machine with several problems per warp (below that, one problem per warp has the shorter evaluation)
+static int tile_lanes(const neo_handle *h, int B, int M)
+{
+    if (M > 4) return 32;
+    const int small = M <= 3 ? 8 : 16;
+    if (h->tile) return h->tile < small ? small : h->tile;
+    return B >= NEO_TILE_MIN_PROBLEMS ? small : 32;
+}
+
 static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 {
     int occ;
-    // kernel variant: sampling schedule (minco_warp.cuh) by trajectory length; the shipped configuration (M = 3) and
-    // the dense-map configuration (M = 10) get instantiations with the piece count as a compile-time constant
+    // kernel variant: lanes per problem (tile_lanes) and sampling schedule (minco_tile.cuh) by trajectory length; one
+    // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
     void (*kern)(const DevParams, const OptArgs) = nullptr;
-    const bool packed = h->min_ctas ? h->min_ctas >= 3 : (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;
-    // staged sums only where parking all pieces would cost the third CTA its shared memory (M = 4: 3 x 80 KB > 227 KB;
-    // measured +21 % there, +1 % at M = 3, -4 % at M = 2: scripts/gpu_ab_min_ctas.py staged)
-    const bool staged = packed && a.M <= 4 && (h->staged > 0 || (h->staged < 0 && 3 * (smem_bytes(a.M) + 1024) > (size_t)227 * 1024));
-#define NEO_K(MODE, MC) (packed ? k_optimize<MODE, MC, 3> : k_optimize<MODE, MC, NEO_MIN_CTAS>)
-#define NEO_KP(MC) (staged ? k_optimize<SAMPLE_BY_PIECE_STAGED, MC, 3> : NEO_K(SAMPLE_BY_PIECE, MC))
-    switch (a.M) {      // one instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
-        case 2: kern = NEO_KP(2); break;
-        case 3: kern = NEO_KP(3); break;
-        case 4: kern = NEO_KP(4); break;
-        case 5: kern = NEO_K(SAMPLE_ALL_PIECES, 5); break;
-        case 6: kern = NEO_K(SAMPLE_ALL_PIECES, 6); break;
-        case 7: kern = NEO_K(SAMPLE_ALL_PIECES, 7); break;
-        case 8: kern = NEO_K(SAMPLE_ALL_PIECES, 8); break;
-        case 9: kern = NEO_K(SAMPLE_ALL_PIECES, 9); break;
-        case 10: kern = NEO_K(SAMPLE_ALL_PIECES, 10); break;
+    const int TL = tile_lanes(h, a.B, a.M);
+    const bool packed = (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;
+    const bool staged = TL < 32;        // shared tiles: one staging block per tile (shared memory is what limits occupancy)
+#define NEO_KW(MODE, MC) (packed ? k_optimize<MODE, MC, 32, 3> : k_optimize<MODE, MC, 32, 2>)
+    switch (a.M) {
+        case 2: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 8, 2> : TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 16, 2> : NEO_KW(SAMPLE_BY_PIECE, 2); break;
+        case 3: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 8, 2> : TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 16, 2> : NEO_KW(SAMPLE_BY_PIECE, 3); break;
+        case 4: kern = TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 4, 16, 2> : NEO_KW(SAMPLE_BY_PIECE, 4); break;
+        case 5: kern = NEO_KW(SAMPLE_ALL_PIECES, 5); break;
+        case 6: kern = NEO_KW(SAMPLE_ALL_PIECES, 6); break;
+        case 7: kern = NEO_KW(SAMPLE_ALL_PIECES, 7); break;
+        case 8: kern = NEO_KW(SAMPLE_ALL_PIECES, 8); break;
+        case 9: kern = NEO_KW(SAMPLE_ALL_PIECES, 9); break;
+        case 10: kern = NEO_KW(SAMPLE_ALL_PIECES, 10); break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
-#undef NEO_K
-#undef NEO_KP
-    // EXPERIMENTAL: speculative restarts (lbfgs_warp.cuh) -- latency-bound launches of the shipped piece count only
-    const bool shadow = h->shadow && !packed && !h->lockstep && a.M == 3 && (size_t)a.B * a.max_attempts <= 16384;
-    if (shadow) kern = k_optimize<SAMPLE_BY_PIECE, 3, NEO_MIN_CTAS, true>;
-    int rc = prep_kernel(h, kern, a.M, &occ, staged);
+#undef NEO_KW
+    const size_t smem = smem_bytes(a.M, TL, staged);
+    int rc = prep_kernel(h, kern, smem, &occ);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
-    const size_t need = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const size_t per_cta = (size_t)WARPS_PER_CTA * (32 / TL);
+    const size_t need = (tasks + per_cta - 1) / per_cta;
     const int grid = (int)(need < (size_t)occ * h->sm_count ? need : (size_t)occ * h->sm_count);
     // per-task scratch records + per-problem state word (library-owned, grow-only)
     char *base;
@@ -807,19 +820,9 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.t_info = (int32_t *)(base + o_i); a.p_state = (unsigned *)(base + o_p);
     a.maps = h->d_maps;
     a.counter = h->d_counter;
-    a.lockstep = h->lockstep;
-    a.slots = nullptr; a.n_resolved = h->d_counter + 1; a.req_bits = nullptr;
-    if (shadow) {
-        const size_t words = (tasks + 31) / 32, slot_bytes = (sizeof(ShadowSlot) * tasks + 255) & ~(size_t)255;
-        char *sb;
-        if ((rc = dev_buf(h, 8, slot_bytes + sizeof(unsigned) * words, (void **)&sb))) return rc;
-        a.slots = (ShadowSlot *)sb; a.req_bits = (unsigned *)(sb + slot_bytes);
-        CK(cudaMemsetAsync(sb, 0, slot_bytes + sizeof(unsigned) * words, st));
-        CK(cudaMemsetAsync(a.n_resolved, 0, sizeof(unsigned int), st));
-    }
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
-    kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M, staged), st>>>(dev_params(h->cfg), a);
+    kern<<<grid, WARPS_PER_CTA * 32, smem, st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
@@ -829,24 +832,27 @@ static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
 {
     int occ;
     void (*kern)(const DevParams, const EvalArgs) = nullptr;
+    const int TL = tile_lanes(h, a.B, a.M);
     switch (a.M) {
-        case 2: kern = k_eval<SAMPLE_BY_PIECE, 2>; break;
-        case 3: kern = k_eval<SAMPLE_BY_PIECE, 3>; break;
-        case 4: kern = k_eval<SAMPLE_BY_PIECE, 4>; break;
-        case 5: kern = k_eval<SAMPLE_ALL_PIECES, 5>; break;
-        case 6: kern = k_eval<SAMPLE_ALL_PIECES, 6>; break;
-        case 7: kern = k_eval<SAMPLE_ALL_PIECES, 7>; break;
-        case 8: kern = k_eval<SAMPLE_ALL_PIECES, 8>; break;
-        case 9: kern = k_eval<SAMPLE_ALL_PIECES, 9>; break;
-        case 10: kern = k_eval<SAMPLE_ALL_PIECES, 10>; break;
+        case 2: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 2, 8> : TL == 16 ? k_eval<SAMPLE_BY_PIECE, 2, 16> : k_eval<SAMPLE_BY_PIECE, 2, 32>; break;
+        case 3: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 3, 8> : TL == 16 ? k_eval<SAMPLE_BY_PIECE, 3, 16> : k_eval<SAMPLE_BY_PIECE, 3, 32>; break;
+        case 4: kern = TL == 16 ? k_eval<SAMPLE_BY_PIECE, 4, 16> : k_eval<SAMPLE_BY_PIECE, 4, 32>; break;
+        case 5: kern = k_eval<SAMPLE_ALL_PIECES, 5, 32>; break;
+        case 6: kern = k_eval<SAMPLE_ALL_PIECES, 6, 32>; break;
+        case 7: kern = k_eval<SAMPLE_ALL_PIECES, 7, 32>; break;
+        case 8: kern = k_eval<SAMPLE_ALL_PIECES, 8, 32>; break;
+        case 9: kern = k_eval<SAMPLE_ALL_PIECES, 9, 32>; break;
+        case 10: kern = k_eval<SAMPLE_ALL_PIECES, 10, 32>; break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
-    int rc = prep_kernel(h, kern, a.M, &occ);
+    const size_t smem = smem_bytes(a.M, TL);
+    int rc = prep_kernel(h, kern, smem, &occ);
     if (rc) return rc;
-    const int need = (a.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int per_cta = WARPS_PER_CTA * (32 / TL);
+    const int need = (a.B + per_cta - 1) / per_cta;
     const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
     a.maps = h->d_maps;
-    kern<<<grid, WARPS_PER_CTA * 32, smem_bytes(a.M), st>>>(dev_params(h->cfg), a);
+    kern<<<grid, WARPS_PER_CTA * 32, smem, st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
@@ -895,6 +901,7 @@ extern "C" int neo_eval(neo_handle *h, int B, int M, const double *x, const doub
     if (rc) return rc;
     if (!x || !head || !tail || !costs || !grad || !status) return fail(h, "neo_eval: null pointer");
     if (B == 0) return NEO_OK;
+    if ((rc = check_map_ids(h, B, map_ids, "neo_eval"))) return rc;
     CK(cudaSetDevice(h->device));
     const size_t n = 3 * M - 2, N2 = 12 * M, b = B;
     for (int pass = 0; pass < 2; pass++) {
@@ -959,11 +966,21 @@ extern "C" int neo_T2tau(const neo_config *cfg, int n, const double *ts, double 
 }
 
 // internal: device pointers, tau-form inputs
+struct TraceDev {
+    int cap = 0;
+    double *x = nullptr, *f = nullptr, *g = nullptr, *costs = nullptr;
+    int32_t *status = nullptr, *len = nullptr;
+};
+
 static int optimize_dev_impl(neo_handle *h, int B, int M, const double *x0, const int32_t *x0_status, const double *head,
                              const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_tau,
-                             int retry_status, int max_attempts, const neo_result *out, cudaStream_t st)
+                             int retry_status, int max_attempts, const neo_result *out, cudaStream_t st,
+                             const TraceDev *tr = nullptr)
 {
     OptArgs a;
+    a.trace_cap = tr ? tr->cap : 0;
+    a.tr_x = tr ? tr->x : nullptr; a.tr_f = tr ? tr->f : nullptr; a.tr_g = tr ? tr->g : nullptr;
+    a.tr_costs = tr ? tr->costs : nullptr; a.tr_status = tr ? tr->status : nullptr; a.tr_len = tr ? tr->len : nullptr;
     a.B = B; a.M = M; a.max_attempts = max_attempts;
     a.x0 = x0; a.x0_status = x0_status; a.head = head; a.tail = tail; a.map_ids = map_ids;
     a.retry_q = retry_q; a.retry_tau = retry_tau; a.retry_status = retry_status;
@@ -999,9 +1016,15 @@ extern "C" int neo_optimize_dev(neo_handle *h, int B, int M, const double *x0, c
                              out, stream ? (cudaStream_t)stream : h->stream);
 }
 
-extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
-                            const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
-                            int max_attempts, neo_result *out)
+struct TraceHost {
+    int cap;
+    double *x, *f, *g, *costs;
+    int32_t *status, *len;
+};
+
+static int optimize_host(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
+                         const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
+                         int max_attempts, neo_result *out, const TraceHost *trace)
 {
     if (!h) return NEO_ERR_INVALID;
     std::lock_guard<std::mutex> g(h->mu);
@@ -1010,7 +1033,10 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
     if (!q0 || !ts0 || !head || !tail || !result_complete(out)) return fail(h, "neo_optimize: null pointer");
     if (max_attempts < 1 || max_attempts > NEO_MAX_ATTEMPTS) return fail(h, "max_attempts out of range");
     if (max_attempts > 1 && (!retry_q || !retry_ts)) return fail(h, "retry arrays required when max_attempts > 1");
+    if (trace && (trace->cap < 1 || !trace->x || !trace->f || !trace->g || !trace->costs || !trace->status || !trace->len))
+        return fail(h, "neo_optimize_trace: null trace array");
     if (B == 0) return NEO_OK;
+    if ((rc = check_map_ids(h, B, map_ids, "neo_optimize"))) return rc;
     CK(cudaSetDevice(h->device));
     const size_t n = 3 * M - 2, nq = 2 * (M - 1), N2 = 12 * M, b = B, A1 = max_attempts - 1;
 
@@ -1063,13 +1089,38 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
     d.status = (int32_t *)(dbase + L.status); d.ok = (int32_t *)(dbase + L.ok); d.attempt = (int32_t *)(dbase + L.attempt);
     d.nit = (int32_t *)(dbase + L.nit); d.runs = (int32_t *)(dbase + L.runs); d.nfev = (int32_t *)(dbase + L.nfev);
     d.work = out->work ? (int64_t *)(dbase + L.work) : nullptr;
+    TraceDev td;
+    size_t tr_tasks = 0;
+    if (trace) {      // test path: the per-task evaluation trace lives in its own device buffer
+        tr_tasks = b * max_attempts;
+        const size_t cap = trace->cap;
+        Carver c{nullptr};
+        for (int pass = 0; pass < 2; pass++) {
+            c.off = 0;
+            td.cap = trace->cap;
+            td.x = c.take<double>(tr_tasks * cap * n); td.g = c.take<double>(tr_tasks * cap * n);
+            td.f = c.take<double>(tr_tasks * cap); td.costs = c.take<double>(tr_tasks * cap * 4);
+            td.status = c.take<int32_t>(tr_tasks * cap); td.len = c.take<int32_t>(tr_tasks);
+            if (!pass) { void *p; if ((rc = dev_buf(h, 8, c.off + 256, &p))) return rc; c.base = (char *)p; }
+        }
+        CK(cudaMemsetAsync(td.len, 0, sizeof(int32_t) * tr_tasks, st));
+    }
     CK(cudaEventRecord(h->ev0, st));
     rc = optimize_dev_impl(h, B, M, (const double *)(dbase + L.x0), any_bad ? (const int32_t *)(dbase + L.st0) : nullptr,
                            (const double *)(dbase + L.head), (const double *)(dbase + L.tail),
                            map_ids ? (const int32_t *)(dbase + L.ids) : nullptr, A1 ? (const double *)(dbase + L.rq) : nullptr,
-                           A1 ? (const double *)(dbase + L.rtau) : nullptr, rstatus, max_attempts, &d, st);
+                           A1 ? (const double *)(dbase + L.rtau) : nullptr, rstatus, max_attempts, &d, st, trace ? &td : nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, st));
+    if (trace) {
+        const size_t cap = trace->cap;
+        CK(cudaMemcpyAsync(trace->x, td.x, 8 * tr_tasks * cap * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(trace->g, td.g, 8 * tr_tasks * cap * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(trace->f, td.f, 8 * tr_tasks * cap, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(trace->costs, td.costs, 8 * tr_tasks * cap * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(trace->status, td.status, 4 * tr_tasks * cap, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(trace->len, td.len, 4 * tr_tasks, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaMemcpyAsync(hbase + L.x, dbase + L.x, L.end - L.x, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
@@ -1085,6 +1136,22 @@ extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const
     memcpy(out->nfev, hbase + L.nfev, 4 * b);
     if (out->work) memcpy(out->work, hbase + L.work, 8 * b * 4);
     return NEO_OK;
+}
+
+extern "C" int neo_optimize(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
+                            const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
+                            int max_attempts, neo_result *out)
+{
+    return optimize_host(h, B, M, q0, ts0, head, tail, map_ids, retry_q, retry_ts, max_attempts, out, nullptr);
+}
+
+extern "C" int neo_optimize_trace(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
+                                  const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
+                                  int max_attempts, neo_result *out, int trace_cap, double *tr_x, double *tr_f, double *tr_g,
+                                  double *tr_costs, int32_t *tr_status, int32_t *tr_len)
+{
+    const TraceHost t = {trace_cap, tr_x, tr_f, tr_g, tr_costs, tr_status, tr_len};
+    return optimize_host(h, B, M, q0, ts0, head, tail, map_ids, retry_q, retry_ts, max_attempts, out, &t);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1116,7 +1183,7 @@ extern "C" int neo_get_coeffs(neo_handle *h, int B, int M, const double *q, cons
         CK(cudaMemcpyAsync(d_head, head, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_tail, tail, sizeof(double) * b * 6, cudaMemcpyHostToDevice, st));
         int occ;
-        if ((rc = prep_kernel(h, k_coeffs, M, &occ))) return rc;
+        if ((rc = prep_kernel(h, k_coeffs, smem_bytes(M), &occ))) return rc;
         const int need = (B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const int grid = need < occ * h->sm_count ? need : occ * h->sm_count;
         k_coeffs<<<grid, WARPS_PER_CTA * 32, smem_bytes(M), st>>>(B, M, d_q, d_ts, d_head, d_tail, d_c);
@@ -1152,7 +1219,7 @@ extern "C" int neo_sample(neo_handle *h, int B, int M, const double *coeffs, con
         CK(cudaMemcpyAsync(d_c, coeffs, sizeof(double) * b * N2, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_ts, ts, sizeof(double) * b * M, cudaMemcpyHostToDevice, st));
         if (states) CK(cudaMemcpyAsync(d_s, states, sizeof(double) * b * ms * 6, cudaMemcpyHostToDevice, st));
-        dim3 grid(states ? (max_samples + 127) / 128 : 1, B);
+        dim3 grid(states ? (max_samples + 127) / 128 : 1, B < 65535 ? B : 65535);
         k_sample<<<grid, 128, 0, st>>>(B, M, d_c, d_ts, hz, max_samples, states ? d_s : nullptr, d_cnt);
         h->launches++;
         CK(cudaGetLastError());

@@ -45,7 +45,7 @@ class Result(C.Structure):
 
 EXPORTS = ['neo_create', 'neo_destroy', 'neo_set_config', 'neo_last_error', 'neo_device_info', 'neo_set_map_esdf',
            'neo_set_map_occupancy', 'neo_set_map_points', 'neo_get_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
-           'neo_optimize_dev', 'neo_T2tau', 'neo_get_coeffs', 'neo_sample', 'neo_last_kernel_ms', 'neo_fp64_peak',
+           'neo_optimize_dev', 'neo_optimize_trace', 'neo_T2tau', 'neo_get_coeffs', 'neo_sample', 'neo_last_kernel_ms', 'neo_fp64_peak',
            'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host', 'neo_astar', 'neo_astar_dev']
 
 _lib = None
@@ -76,6 +76,7 @@ def load():
         lib.neo_eval_dev.argtypes = [V, I, I, V, V, V, V, V, V, V, V, V, V]
         lib.neo_optimize.argtypes = [V, I, I, V, V, V, V, V, V, V, I, C.POINTER(Result)]
         lib.neo_optimize_dev.argtypes = [V, I, I, V, V, V, V, V, V, V, I, I, C.POINTER(Result), V]
+        lib.neo_optimize_trace.argtypes = [V, I, I, V, V, V, V, V, V, V, I, C.POINTER(Result), I, V, V, V, V, V, V]
         lib.neo_T2tau.argtypes = [C.POINTER(Config), I, V, V, V]
         lib.neo_get_coeffs.argtypes = [V, I, I, V, V, V, V, V]
         lib.neo_sample.argtypes = [V, I, I, V, V, D, I, V, V]
@@ -227,6 +228,27 @@ class Handle:
         self._ck(self.lib.neo_optimize(self.h, B, M, ptr(q0), ptr(ts0), ptr(head), ptr(tail), ptr(ids), ptr(retry_q),
                                        ptr(retry_ts), max_attempts, C.byref(r)))
         return out
+
+    def optimize_trace(self, M, q0, ts0, head, tail, map_ids=None, retry_q=None, retry_ts=None, max_attempts=1, cap=512):
+        """neo_optimize_trace: optimize() plus, per task (attempt * B + problem), the first `cap` evaluations the device
+        made: dict(x (A*B, cap, n), f, g, costs, status, len (A*B)). For the lockstep tests."""
+        q0 = f64(q0); B = q0.shape[0]; n = 3 * M - 2
+        q0 = f64(q0, (B, 2, M - 1)); ts0 = f64(ts0, (B, M))
+        head = f64(pad_state(head), (B, 3, 2)); tail = f64(pad_state(tail), (B, 3, 2))
+        ids = None if map_ids is None else np.ascontiguousarray(map_ids, dtype=np.int32)
+        if max_attempts > 1:
+            retry_q = f64(retry_q, (B, max_attempts - 1, 2, M - 1)); retry_ts = f64(retry_ts, (M,))
+        else:
+            retry_q = retry_ts = None
+        out = self.alloc_result(B, M)
+        r = self.result_struct(out)
+        T = B * max_attempts
+        tr = dict(x=np.zeros((T, cap, n)), f=np.zeros((T, cap)), g=np.zeros((T, cap, n)), costs=np.zeros((T, cap, 4)),
+                  status=np.zeros((T, cap), np.int32), len=np.zeros(T, np.int32))
+        self._ck(self.lib.neo_optimize_trace(self.h, B, M, ptr(q0), ptr(ts0), ptr(head), ptr(tail), ptr(ids), ptr(retry_q),
+                                             ptr(retry_ts), max_attempts, C.byref(r), cap, ptr(tr['x']), ptr(tr['f']),
+                                             ptr(tr['g']), ptr(tr['costs']), ptr(tr['status']), ptr(tr['len'])))
+        return out, tr
 
     def T2tau(self, ts):
         ts = f64(ts); tau = np.zeros_like(ts); st = np.zeros(ts.size, np.int32)
