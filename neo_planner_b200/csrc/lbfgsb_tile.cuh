@@ -32,9 +32,20 @@ namespace neo {
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+// division and square root expand to ~15 instructions plus a slow path each; with some 60 call sites in the optimizer they
+// are kept out of line so that the hot loop fits the instruction cache (profiles/r2_summary.md: 50 % of the stall samples
+// of the first version of this file were instruction fetches)
+__device__ __noinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __noinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+__device__ __noinline__ double nrm2_x87(int n, const double *v) { return x87_nrm2(n, v); }
 __device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+// a / b, correctly rounded, given rb = RN(1 / b): q = RN(a rb), then one fused correction with the exact residual
+// (Markstein's theorem; operands here are in the normal range; checked against the hardware division on 4e8 random pairs)
+__device__ __forceinline__ double xdiv_r(double a, double b, double rb)
+{
+    const double q = __dmul_rn(a, rb);
+    return __fma_rn(__fma_rn(-b, q, a), rb, q);
+}
 
 struct Dcsrch {
     bool brackt;
@@ -136,7 +147,7 @@ __device__ __forceinline__ void dcsrch_start(Dcsrch &S, double stp, double f, do
 }
 
 // 0 = evaluate at stp, 1 = CONVERGENCE, 2 = WARNING
-__device__ __forceinline__ int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
+__device__ __noinline__ int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
 {
     const double ftest = xadd(S.finit, xmul(stp, S.gtest));
     int task = 0;
@@ -170,7 +181,7 @@ __device__ __forceinline__ int dcsrch_step(Dcsrch &S, double &stp, double f, dou
 
 // ---- BLAS kernels restated (see the header of this file and oracle/minco_oracle.c) ------------------------------------
 // ddot: n < 16 fused multiply-adds in index order; 16 <= n < 32: the first 16 products rounded, four lanes, fold, then fma
-__device__ __forceinline__ double blas_ddot(int n, const double *a, const double *b)
+__device__ __noinline__ double blas_ddot(int n, const double *a, const double *b)
 {
     double s = 0.0;
     int i = 0;
@@ -182,13 +193,15 @@ __device__ __forceinline__ double blas_ddot(int n, const double *a, const double
         s = xadd(xadd(v[0], v[2]), xadd(v[1], v[3]));
         i = 16;
     }
+#pragma unroll 1
     for (; i < n; i++) s = xfma(a[i], b[i], s);
     return s;
 }
 // a loop written out in scipy's own C: multiply, then add
-__device__ __forceinline__ double loop_dot(int n, const double *a, const double *b)
+__device__ __noinline__ double loop_dot(int n, const double *a, const double *b)
 {
     double s = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) s = xadd(s, xmul(a[i], b[i]));
     return s;
 }
@@ -197,20 +210,22 @@ __device__ __forceinline__ double loop_dot(int n, const double *a, const double 
 __device__ __forceinline__ int wn_col(int j) { return j * (j + 1) / 2; }
 
 // dpotrf (OpenBLAS potf2_U) on the n x n diagonal block starting at row/column o. false: not positive definite.
-template <int TL>
-__device__ __forceinline__ bool lb_potf2(const Tile<TL> &T, double *wn, int o, int n)
+// rd[o + j] receives 1 / u_jj (used again by the triangular solves)
+__device__ __noinline__ bool lb_potf2(int tl, int TL, unsigned mask, double *wn, double *rd, int o, int n)
 {
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
         double *cj = wn + wn_col(o + j) + o;                         // cj[k] = element (o + k, o + j)
         double ajj = xsub(cj[j], blas_ddot(j, cj, cj));
         if (!(ajj > 0.0)) return false;                               // same value in every lane of the tile
         ajj = xsqrt(ajj);
-        T.sync();
-        if (T.tl == 0) cj[j] = ajj;
+        __syncwarp(mask);
+        const double r = xdiv(1.0, ajj);
+        if (tl == 0) { cj[j] = ajj; rd[o + j] = r; }
         if (j < n - 1) {
             const int m1 = j & ~3, k3 = j - m1;
-            const double r = xdiv(1.0, ajj);
-            for (int i = j + 1 + T.tl; i < n; i += TL) {
+#pragma unroll 1
+            for (int i = j + 1 + tl; i < n; i += TL) {
                 double *ci = wn + wn_col(o + i) + o;                 // ci[k] = element (o + k, o + i)
                 double v = ci[j];
                 if (m1) {                                             // dgemv_t kernel: four rows at a time in four lanes
@@ -229,7 +244,7 @@ __device__ __forceinline__ bool lb_potf2(const Tile<TL> &T, double *wn, int o, i
                 ci[j] = xmul(v, r);
             }
         }
-        T.sync();
+        __syncwarp(mask);
     }
     return true;
 }
@@ -255,6 +270,7 @@ __device__ __forceinline__ void lb_update(const Tile<TL> &T, const TileMem &m, i
     if (T.tl == 0) m.dr[slot] = dr;
     T.sync();
     const double *ynew = m.wy + slot * n;
+#pragma unroll 1
     for (int e = T.tl; e < 2 * col; e += TL) {
         if (e < col) {                                                 // row `col` of Y'Y
             const int sj = lb_slot(L, e);
@@ -273,19 +289,23 @@ template <int TL>
 __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, const LbMem &L)
 {
     const int col = L.col;
-    const double theta = L.theta;
-    double *wn = m.wn;
+    const double theta = L.theta, rtheta = xdiv(1.0, theta);
+    double *wn = m.wn, *rd = m.wn + wn_col(LBW) + LBW;
+#pragma unroll 1
     for (int iy = T.tl; iy < col; iy += TL) {
         const int si = lb_slot(L, iy), is = col + iy;
         double *c1 = wn + wn_col(iy), *c2 = wn + wn_col(is);
+#pragma unroll 1
         for (int jy = 0; jy <= iy; jy++) {
             const int sj = lb_slot(L, jy);
-            double v = xdiv(m.yr[si * HIST + sj], theta);                               // Y'Y / theta
+            double v = xdiv_r(m.yr[si * HIST + sj], theta, rtheta);                    // Y'Y / theta
             if (jy == iy) v = xadd(v, m.dr[si]);                                         // + D
             c1[jy] = v;
             c2[col + jy] = 0.0;                                                           // S'AA'S * theta (no active set)
         }
+#pragma unroll 1
         for (int jy = 0; jy < iy; jy++) c2[jy] = -0.0;                                   // -L_a'
+#pragma unroll 1
         for (int jy = iy; jy < col; jy++) {
             const int sj = lb_slot(L, jy);
             c2[jy] = jy == iy ? m.rzd[si] : m.yr[si * HIST + sj];                        // R_z'
@@ -293,24 +313,30 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
     }
     // NOTE the transposition: formk fills wn(jy, is) = R_z(iy, jy) for jy >= iy -- column `is`, rows jy: c2[jy] above.
     T.sync();
-    if (!lb_potf2(T, wn, 0, col)) return false;
+    if (!lb_potf2(T.tl, TL, T.mask, wn, rd, 0, col)) return false;
     if (col == 1) {                                                    // one right-hand side: trsv, a true division
-        if (T.tl == 0) wn[wn_col(1)] = xdiv(wn[wn_col(1)], wn[0]);
+        if (T.tl == 0) wn[wn_col(1)] = xdiv_r(wn[wn_col(1)], wn[0], rd[0]);
     } else {                                                           // blocked trsm kernel: 8, 4, 2, 1 rows
+#pragma unroll 1
         for (int c = col + T.tl; c < 2 * col; c += TL) {
             double *b = wn + wn_col(c);
             int kk = 0;
+#pragma unroll 1
             for (int bs = 8; bs > 0; bs >>= 1) {
                 if (!(col & bs)) continue;
                 if (kk > 0)
+#pragma unroll 1
                     for (int i = kk; i < kk + bs; i++) {
                         const double *ui = wn + wn_col(i);
                         double acc = 0.0;
+#pragma unroll 1
                         for (int k = 0; k < kk; k++) acc = xfma(ui[k], b[k], acc);
                         b[i] = xsub(b[i], acc);
                     }
+#pragma unroll 1
                 for (int i = kk; i < kk + bs; i++) {
-                    b[i] = xmul(b[i], xdiv(1.0, wn[wn_col(i) + i]));
+                    b[i] = xmul(b[i], rd[i]);
+#pragma unroll 1
                     for (int k = i + 1; k < kk + bs; k++) b[k] = xfma(-b[i], wn[wn_col(k) + i], b[k]);
                 }
                 kk += bs;
@@ -318,13 +344,15 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
         }
     }
     T.sync();
+#pragma unroll 1
     for (int js = col; js < 2 * col; js++) {
         const double *cjs = wn + wn_col(js);
+#pragma unroll 1
         for (int is = col + T.tl; is <= js; is += TL)
             wn[wn_col(js) + is] = xadd(wn[wn_col(js) + is], blas_ddot(col, wn + wn_col(is), cjs));
     }
     T.sync();
-    return lb_potf2(T, wn, col, col);
+    return lb_potf2(T.tl, TL, T.mask, wn, rd, col, col);
 }
 
 // subsm with r = -g: returns the lane-owned component of the subspace step
@@ -332,11 +360,12 @@ template <int TL>
 __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, int n, const LbMem &L, double g)
 {
     const int col = L.col, m2 = 2 * col;
-    const double theta = L.theta;
-    double *wn = m.wn, *wv = m.wn + wn_col(LBW);
+    const double theta = L.theta, rtheta = xdiv(1.0, theta);
+    double *wn = m.wn, *wv = m.wn + wn_col(LBW), *rd = wv + LBW;
     double d = -g;
     if (T.tl < n) m.dv[T.tl] = d;
     T.sync();
+#pragma unroll 1
     for (int e = T.tl; e < m2; e += TL)
         wv[e] = e < col ? loop_dot(n, m.wy + lb_slot(L, e) * n, m.dv) : xmul(theta, loop_dot(n, m.ws + lb_slot(L, e - col) * n, m.dv));
     T.sync();
@@ -347,6 +376,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
         double s[RPL];
 #pragma unroll
         for (int q = 0; q < RPL; q++) s[q] = 0.0;
+#pragma unroll 1
         for (int k = 0; k < m2; k++) {
             if ((k & (TL - 1)) == T.tl) {
                 double v = wv[k];
@@ -356,7 +386,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
                     for (int q = 1; q < RPL; q++) if (k / TL == q) sk = s[q];
                     v = xsub(v, sk);
                 }
-                wv[k] = xdiv(v, wn[wn_col(k) + k]);
+                wv[k] = xdiv_r(v, wn[wn_col(k) + k], rd[k]);
             }
             T.sync();
             const double bk = wv[k];
@@ -372,23 +402,27 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
         }
     }
     T.sync();
+#pragma unroll 1
     for (int i = T.tl; i < col; i += TL) wv[i] = -wv[i];
     T.sync();
     // trsv, not transposed: b_i /= u_ii, then b_k = fma(-b_i, u_ki, b_k)
+#pragma unroll 1
     for (int i = m2 - 1; i >= 0; i--) {
         const double *ui = wn + wn_col(i);
-        if (T.tl == 0) wv[i] = xdiv(wv[i], ui[i]);
+        if (T.tl == 0) wv[i] = xdiv_r(wv[i], ui[i], rd[i]);
         T.sync();
         const double t = -wv[i];
+#pragma unroll 1
         for (int k = T.tl; k < i; k += TL) wv[k] = xfma(t, ui[k], wv[k]);
         T.sync();
     }
     if (T.tl < n) {
+#pragma unroll 1
         for (int jy = 0; jy < col; jy++) {
             const int sj = lb_slot(L, jy);
-            d = xadd(xadd(d, xdiv(xmul(m.wy[sj * n + T.tl], wv[jy]), theta)), xmul(m.ws[sj * n + T.tl], wv[col + jy]));
+            d = xadd(xadd(d, xdiv_r(xmul(m.wy[sj * n + T.tl], wv[jy]), theta, rtheta)), xmul(m.ws[sj * n + T.tl], wv[col + jy]));
         }
-        d = xmul(d, xdiv(1.0, theta));
+        d = xmul(d, rtheta);
     }
     T.sync();
     return d;
@@ -471,7 +505,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             T.sync();
             if (mine) m.dv[T.tl] = y;
             T.sync();
-            const double nr = x87_nrm2(n, m.dv);
+            const double nr = nrm2_x87(n, m.dv);
             const double rr = xmul(nr, nr);
             double dr, ddum, s;
             if (o.stp == 1.0) { dr = xsub(o.gd, o.gdold); ddum = -o.gdold; s = o.d; }
@@ -491,7 +525,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             T.sync();
             if (mine) m.dv[T.tl] = o.d;
             T.sync();
-            const double dnorm = x87_nrm2(n, m.dv);
+            const double dnorm = nrm2_x87(n, m.dv);
             o.stp = (o.nit == 0) ? fmin(xdiv(1.0, dnorm), LS_STPMAX) : 1.0;
             o.t = o.x; o.r = o.g; o.fold = o.f;
             o.gd = opt_gd(T, m, n, o.g, o.d);

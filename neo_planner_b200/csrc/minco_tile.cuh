@@ -42,7 +42,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif
 constexpr int HIST = 10;        // L-BFGS memory (maxcor, EP:220)
 constexpr int LBW = 2 * HIST;   // order of the middle matrix of the compact representation
-constexpr int WN_DOUBLES = LBW * (LBW + 1) / 2 + LBW + 2;    // packed upper triangle + the subspace vector wv
+constexpr int WN_DOUBLES = LBW * (LBW + 1) / 2 + 2 * LBW + 2;    // packed upper triangle + the subspace vector wv + 1/diagonal
 
 struct DevParams {
     double v_max2, T_min, T_max, safe_dis, dt;

@@ -24,7 +24,8 @@ using namespace neo;
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
 #ifndef NEO_TILE_MIN_PROBLEMS
-#define NEO_TILE_MIN_PROBLEMS 4096   // batch size from which short trajectories (M <= 4) run several problems per warp
+#define NEO_TILE_MIN_PROBLEMS 8192   // batch size from which short trajectories (M <= 4) run several problems per warp
+                                     // (measured break-even on B200: 4 k problems 5.2 vs 4.5 ms, 16 k 11.4 vs 12.9 ms)
 #endif
 #ifndef NEO_PACKED_MIN_PER_SM
 #define NEO_PACKED_MIN_PER_SM 324    // problems x pieces per SM from which the 3-CTAs-per-SM instantiation is launched
@@ -776,7 +777,7 @@ static int tile_lanes(const neo_handle *h, int B, int M)
 {
     if (M > 4) return 32;
     const int small = M <= 3 ? 8 : 16;
-    if (h->tile) return h->tile < small ? small : h->tile;
+    if (h->tile) return h->tile == 32 ? 32 : small;
     return B >= NEO_TILE_MIN_PROBLEMS ? small : 32;
 }
 
@@ -787,19 +788,22 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
     void (*kern)(const DevParams, const OptArgs) = nullptr;
     const int TL = tile_lanes(h, a.B, a.M);
-    const bool packed = (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;
+    const bool packed = (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;    // M >= 5: 3 CTAs per SM
+    (void)packed;
     const bool staged = TL < 32;        // shared tiles: one staging block per tile (shared memory is what limits occupancy)
 #define NEO_KW(MODE, MC) (packed ? k_optimize<MODE, MC, 32, 3> : k_optimize<MODE, MC, 32, 2>)
     switch (a.M) {
-        case 2: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 8, 2> : TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 16, 2> : NEO_KW(SAMPLE_BY_PIECE, 2); break;
-        case 3: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 8, 2> : TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 16, 2> : NEO_KW(SAMPLE_BY_PIECE, 3); break;
-        case 4: kern = TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 4, 16, 2> : NEO_KW(SAMPLE_BY_PIECE, 4); break;
+#ifndef NEO_FAST_BUILD      // development builds (-DNEO_FAST_BUILD) instantiate M = 3 only
+        case 2: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 8, 2> : k_optimize<SAMPLE_BY_PIECE, 2, 32, 2>; break;
+        case 4: kern = TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 4, 16, 2> : k_optimize<SAMPLE_BY_PIECE, 4, 32, 2>; break;
         case 5: kern = NEO_KW(SAMPLE_ALL_PIECES, 5); break;
         case 6: kern = NEO_KW(SAMPLE_ALL_PIECES, 6); break;
         case 7: kern = NEO_KW(SAMPLE_ALL_PIECES, 7); break;
         case 8: kern = NEO_KW(SAMPLE_ALL_PIECES, 8); break;
         case 9: kern = NEO_KW(SAMPLE_ALL_PIECES, 9); break;
         case 10: kern = NEO_KW(SAMPLE_ALL_PIECES, 10); break;
+#endif
+        case 3: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 8, 2> : k_optimize<SAMPLE_BY_PIECE, 3, 32, 2>; break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
 #undef NEO_KW
@@ -834,8 +838,8 @@ static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
     void (*kern)(const DevParams, const EvalArgs) = nullptr;
     const int TL = tile_lanes(h, a.B, a.M);
     switch (a.M) {
-        case 2: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 2, 8> : TL == 16 ? k_eval<SAMPLE_BY_PIECE, 2, 16> : k_eval<SAMPLE_BY_PIECE, 2, 32>; break;
-        case 3: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 3, 8> : TL == 16 ? k_eval<SAMPLE_BY_PIECE, 3, 16> : k_eval<SAMPLE_BY_PIECE, 3, 32>; break;
+#ifndef NEO_FAST_BUILD
+        case 2: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 2, 8> : k_eval<SAMPLE_BY_PIECE, 2, 32>; break;
         case 4: kern = TL == 16 ? k_eval<SAMPLE_BY_PIECE, 4, 16> : k_eval<SAMPLE_BY_PIECE, 4, 32>; break;
         case 5: kern = k_eval<SAMPLE_ALL_PIECES, 5, 32>; break;
         case 6: kern = k_eval<SAMPLE_ALL_PIECES, 6, 32>; break;
@@ -843,6 +847,8 @@ static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
         case 8: kern = k_eval<SAMPLE_ALL_PIECES, 8, 32>; break;
         case 9: kern = k_eval<SAMPLE_ALL_PIECES, 9, 32>; break;
         case 10: kern = k_eval<SAMPLE_ALL_PIECES, 10, 32>; break;
+#endif
+        case 3: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 3, 8> : k_eval<SAMPLE_BY_PIECE, 3, 32>; break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
     const size_t smem = smem_bytes(a.M, TL);

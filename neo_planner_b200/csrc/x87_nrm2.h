@@ -9,8 +9,10 @@
 
 #if defined(__CUDACC__)
 #define X87_FN __host__ __device__ __forceinline__
+#define X87_NOINLINE __host__ __device__ __noinline__
 #else
 #define X87_FN static inline
+#define X87_NOINLINE static __attribute__((noinline))
 #endif
 
 namespace neo {
@@ -111,11 +113,15 @@ X87_FN Ext x87_sqrt(Ext a)
     double rs = __builtin_sqrt(est);
 #endif
     uint64_t r = rs >= 18446744073709551615.0 ? 0xffffffffffffffffull : (uint64_t)rs;
-    for (int it = 0; it < 2; it++) {
-        if (r == 0) break;
-        const unsigned __int128 q = N / r;
-        const unsigned __int128 s = ((unsigned __int128)r + q) >> 1;
-        r = s > (unsigned __int128)0xffffffffffffffffull ? 0xffffffffffffffffull : (uint64_t)s;
+    {   // one Newton step with the residual N - r^2 formed exactly (|residual| < 2^78) and divided in floating point
+        const unsigned __int128 sq = (unsigned __int128)r * r;
+        const bool neg = sq > N;
+        const unsigned __int128 mag = neg ? sq - N : N - sq;
+        const double magd = (double)(uint64_t)(mag >> 64) * 18446744073709551616.0 + (double)(uint64_t)mag;
+        const double stepd = magd / (2.0 * (double)r);
+        const uint64_t step = (uint64_t)(stepd + 0.5);
+        if (neg) r -= step;
+        else r = (0xffffffffffffffffull - r < step) ? 0xffffffffffffffffull : r + step;
     }
     while ((unsigned __int128)r * r > N) r--;
     while (r != 0xffffffffffffffffull && (unsigned __int128)(r + 1) * (r + 1) <= N) r++;
@@ -153,13 +159,63 @@ X87_FN double x87_to_double(Ext a)
     return c.d;
 }
 
-// dnrm2 of v[0..n), elements taken in index order
-X87_FN double x87_nrm2(int n, const double *v)
+// dnrm2 of v[0..n), elements taken in index order -- the operations exactly as the x87 performs them
+X87_NOINLINE double x87_nrm2_exact(int n, const double *v)
 {
     Ext s;
     s.m = 0; s.e = 0;
     for (int i = 0; i < n; i++) s = x87_add(s, x87_sqr(x87_from_double(v[i])));
     return x87_to_double(x87_sqrt(s));
+}
+
+X87_FN double x87_fma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
+// Same value, usually without the emulation. The x87 result differs from the exact norm by less than (n + 2) * 2^-64
+// relative before its final rounding to double, i.e. by less than 2^-6 ulp of the result for n <= 60. The norm is
+// therefore computed to ~100 bits in double-double arithmetic; whenever it lies further than 2^-6 ulp from every
+// rounding boundary, the correctly rounded double IS the x87's answer. Only the remaining ~3 % of the calls (and
+// denormal / huge magnitudes) go through x87_nrm2_exact.
+X87_FN double x87_nrm2(int n, const double *v)
+{
+    double hi = 0.0, lo = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double a = v[i];
+        const double p = a * a, pe = x87_fma(a, a, -p);            // a^2 = p + pe exactly
+        const double t = hi + p, bb = t - hi;                       // two-sum
+        const double err = (hi - (t - bb)) + (p - bb);
+        hi = t; lo += err + pe;
+    }
+    {   // renormalise
+        const double t = hi + lo;
+        lo = lo - (t - hi); hi = t;
+    }
+    union { double d; uint64_t u; } c;
+    c.d = hi;
+    const int ex = (int)((c.u >> 52) & 0x7ff);
+    if (ex < 120 || ex > 1900) return x87_nrm2_exact(n, v);         // zero, denormal squares, overflow range
+#if defined(__CUDA_ARCH__)
+    const double r = __dsqrt_rn(hi);
+#else
+    const double r = __builtin_sqrt(hi);
+#endif
+    const double res = x87_fma(-r, r, hi) + lo;                      // hi - r^2 is exact for a correctly rounded root
+    const double rlo = res / (2.0 * r);
+    c.d = r;
+    if ((c.u & 0x000fffffffffffffull) == 0) return x87_nrm2_exact(n, v);    // power of two: uneven neighbour spacing
+    c.u &= 0x7ff0000000000000ull;
+    const double ulp = c.d * 2.220446049250313e-16;                  // 2^(e - 52)
+    const double q = rlo / ulp;
+    const double aq = q < 0.0 ? -q : q;
+    if (aq < 0.5 - 0.015625) return r;
+    if (aq > 0.5 + 0.015625 && aq < 1.0) return q > 0.0 ? r + ulp : r - ulp;
+    return x87_nrm2_exact(n, v);
 }
 
 }  // namespace neo

@@ -7,7 +7,7 @@ from neo_planner_b200 import lib
 from bench import workload
 
 res = {}
-for name, sizes in (('c2', [1024]), ('c4', [4096, 16384, 65536])):
+for name, sizes in ((('c2', [1024]), ('c4', [4096, 16384, 65536])) if not os.environ.get('AB_C4_ONLY') else (('c4', [16384, 65536]),)):
     wl_full = workload(name, 0, 1)
     for B in sizes:
         sl = slice(0, B)

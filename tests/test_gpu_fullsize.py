@@ -1,14 +1,60 @@
-"""Full-size runs (BASELINE.json configs 4 and 5) checked through size-independent properties, since the CPU checkers
-cannot finish these sizes in test time: determinism, independence of batch composition and order, agreement of the
-speculative retry scheduler with plain sequential semantics, and the invariants every MINCO trajectory must satisfy
-(boundary states, C^4 continuity at the waypoints, durations inside (T_min, T_max), collision tolerance)."""
+"""Full-size runs (BASELINE.json configs 4 and 5): every problem against the CPU checker (all host threads), plus the
+size-independent properties -- determinism, independence of batch composition and order, agreement of the speculative
+retry scheduler with plain sequential semantics, and the invariants every MINCO trajectory must satisfy (boundary
+states, C^4 continuity at the waypoints, durations inside (T_min, T_max), collision tolerance)."""
+import os
+
 import numpy as np
 import pytest
 
 from neo_planner_b200 import guesses, lib
 from neo_planner_b200.worlds import make_world, make_problems, YamlConfig
+from oracle import c_oracle
 
 pytestmark = pytest.mark.gpu
+
+
+def pinned_handle(cfg, n_maps, tile):
+    """A handle whose lanes-per-problem choice does not depend on the batch size (NEO_TILE is read at neo_create)."""
+    old = os.environ.get('NEO_TILE')
+    os.environ['NEO_TILE'] = str(tile)
+    try:
+        return lib.Handle(cfg, 0, n_maps)
+    finally:
+        if old is None:
+            del os.environ['NEO_TILE']
+        else:
+            os.environ['NEO_TILE'] = old
+
+
+def compare_with_checker(cfg, M, worlds, ids, head, tail, q0, ts0, rq, rts, out, sel, floor):
+    """Device results `out` (all problems) vs the multithreaded C checker on the problems `sel`."""
+    maps = [c_oracle.OracleMap.from_world(w) for w in worlds]
+    p = c_oracle.Params.from_config(cfg)
+    ref = c_oracle.plan_batch_mt(p, maps, M, head[sel], tail[sel], q0[sel], ts0[sel], rq[sel], rts, 5,
+                                 map_ids=None if ids is None else ids[sel])
+    n = len(ref['ok'])
+    same_path = ((out['ok'][sel] == ref['ok']) & (out['runs'][sel] == ref['runs']) & (out['nit'][sel] == ref['nit'])
+                 & (out['status'][sel] == ref['status']) & (out['attempt'][sel] == ref['attempt']))
+    dc = np.max(np.abs(out['coeffs'][sel] - ref['coeffs']).reshape(n, -1), axis=1)
+    good = same_path & (dc <= 1e-4)
+    both_ok = (out['ok'][sel] == 1) & (ref['ok'] == 1)
+    w = np.asarray(cfg.weights, dtype=float)
+    fd, fr = out['costs'][sel] @ w, ref['costs'] @ w
+    rel = np.abs(fd - fr) / np.maximum(np.abs(fr), 1e-300)
+    diff = ~good & both_ok
+    print(f'M={M}: {int(good.sum())}/{n} problems identical to the checker (same attempt, status, iterations; coefficients <= 1e-4 m; '
+          f'worst among them {dc[good].max():.2e} m); ok-flag agreement {np.mean(out["ok"][sel] == ref["ok"]):.5f}; of the {int((~good).sum())} others '
+          f'{int(diff.sum())} are accepted by both sides with final cost ratio device/checker median {np.median(fd[diff] / fr[diff]) if diff.any() else 1:.4f} '
+          f'(p10 {np.percentile(fd[diff] / fr[diff], 10) if diff.any() else 1:.3f}, p90 {np.percentile(fd[diff] / fr[diff], 90) if diff.any() else 1:.3f})')
+    assert good.mean() >= floor
+    # same final decision vector bit for bit (the common case) and a converged exit (the last evaluated point is the
+    # returned one, EP:233): the four cost terms must agree to rounding -- north_star: cost within 1e-6 relative
+    samex = good & np.all(out['x'][sel] == ref['x'], axis=1) & (ref['status'] <= 1)
+    print(f'      {int(samex.sum())} of them end in a bit-identical decision vector on a converged exit; worst relative cost difference there '
+          f'{rel[samex].max():.1e}')
+    assert samex.sum() >= 0.5 * n and rel[samex].max() <= 1e-9
+    return good
 
 
 def derivs(c, T):
@@ -52,10 +98,11 @@ def check_invariants(cfg, M, head, tail, out):
 def test_config4_65536_problems_256_worlds():
     cfg = YamlConfig(); M = 3
     n_worlds, per = 256, 256
-    h = lib.Handle(cfg, 0, n_worlds)
-    heads, tails = [], []
+    h = pinned_handle(cfg, n_worlds, 8)          # 4 problems per warp: what a batch of this size runs by default
+    heads, tails, worlds = [], [], []
     for wid in range(n_worlds):
         w = make_world(wid)
+        worlds.append(w)
         h.set_map_occupancy(wid, w.H, w.W, w.res, w.ox, w.oy, w.occ)
         a, b = make_problems(w, per)
         heads.append(a); tails.append(b)
@@ -66,6 +113,8 @@ def test_config4_65536_problems_256_worlds():
     out = h.optimize(M, q0, ts0, head, tail, ids, rq, rts, 5)
     assert out['ok'].mean() > 0.85
     check_invariants(cfg, M, head, tail, out)
+    # every one of the 65,536 problems against the CPU checker
+    compare_with_checker(cfg, M, worlds, ids, head, tail, q0, ts0, rq, rts, out, np.arange(B), 0.985)
     # determinism: warps pick tasks in a different order every launch; results must not depend on it
     again = h.optimize(M, q0, ts0, head, tail, ids, rq, rts, 5)
     for k in ('x', 'ts', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):
@@ -77,6 +126,16 @@ def test_config4_65536_problems_256_worlds():
     for k in ('x', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):
         assert np.array_equal(part[k], out[k][sub]), k
     # speculative retries keep sequential semantics: where attempt 0 is accepted, a 1-attempt run returns the same thing
+    # one problem per warp (what a small batch runs) on the same subset: same algorithm, different partial-sum order
+    h32 = pinned_handle(cfg, n_worlds, 32)
+    for wid in sorted(set(ids[sub].tolist())):
+        w = worlds[wid]
+        h32.set_map_occupancy(wid, w.H, w.W, w.res, w.ox, w.oy, w.occ)
+    wide = h32.optimize(M, q0[sub], ts0[sub], head[sub], tail[sub], ids[sub], rq[sub], rts, 5)
+    agree = ((wide['ok'] == part['ok']) & (wide['nit'] == part['nit']) & (wide['attempt'] == part['attempt'])
+             & (np.max(np.abs(wide['coeffs'] - part['coeffs']).reshape(len(sub), -1), axis=1) <= 1e-4))
+    print(f'8 vs 32 lanes per problem: {int(agree.sum())}/{len(sub)} identical outcomes')
+    assert agree.mean() >= 0.985
     one = h.optimize(M, q0, ts0, head, tail, ids, max_attempts=1)
     first = out['attempt'] == 0
     assert first.mean() > 0.7
@@ -97,6 +156,8 @@ def test_config5_dense_map_10_pieces():
     out = h.optimize(M, q0, ts0, head, tail, None, rq, rts, 5)
     assert out['ok'].mean() > 0.7
     check_invariants(cfg, M, head, tail, out)
+    # every one of the 16,384 problems against the CPU checker (~8 ms per plan and core at this size)
+    compare_with_checker(cfg, M, [w], None, head, tail, q0, ts0, rq, rts, out, np.arange(B), 0.97)
     again = h.optimize(M, q0, ts0, head, tail, None, rq, rts, 5)
     for k in ('x', 'coeffs', 'status', 'ok', 'attempt', 'nit', 'nfev'):
         assert np.array_equal(out[k], again[k]), k

@@ -163,11 +163,12 @@ def _cls(msg):
     return 4
 
 
-@pytest.mark.parametrize('name,min_match', [('plans_M3.npz', 0.93), ('plans_M10.npz', 0.85)])
+@pytest.mark.parametrize('name,min_match', [('plans_M3.npz', 0.97), ('plans_M10.npz', 0.95)])
 def test_plan_once_against_reference_golden(golden, name, min_match):
     """plan_once from the expert guess: same termination class and iteration count as scipy's L-BFGS-B in the
     reference, final decision vector within 1e-6 and coefficients within 1e-4 m, on all but the line-search
-    knife-edge problems."""
+    knife-edge problems (every differing outcome is traced to a last-bit difference of f or g by
+    tests/test_gpu_lockstep.py; the floor here is the measured rate minus two problems)."""
     g = golden(name)
     M = int(g['M']); cfg = YamlConfig(); cfg.init_wpts_num = M - 1
     w = make_world(int(g['world_id']))
@@ -213,7 +214,7 @@ def test_plan_with_retries_against_reference_golden(golden):
                 and out['nit'][k] == g['plan_iter'][k])
         agree += int(good)
     print(f'plan(): {agree}/{B} identical outcome (ok flag, runs, iterations, coefficients <= 1e-4 m)')
-    assert agree >= 0.9 * B
+    assert agree >= 0.97 * B
 
 
 @pytest.mark.parametrize('M,B', [(3, 1024), (10, 256)])
@@ -233,7 +234,7 @@ def test_optimize_against_c_oracle(M, B, world0):
     good = same_ok & close & same_path
     print(f'M={M}: {good.sum()}/{B} identical to the CPU checker (ok {same_ok.mean():.3f}, coeffs<=1e-4 {close.mean():.3f}, '
           f'same path {same_path.mean():.3f}); ok rate {out["ok"].mean():.3f}; mean nfev {out["nfev"].mean():.1f}')
-    assert good.mean() >= 0.93
+    assert good.mean() >= 0.975
     # size-independent properties on every problem: trajectory endpoints and continuity
     ok = out['ok'] == 1
     c = out['coeffs'][ok]; ts = out['ts'][ok]
@@ -340,7 +341,7 @@ def test_plan_against_scipy_on_unseen_problems():
         agree += int(np.max(np.abs(c - out['coeffs'][k])) <= 1e-4 and opt.iter_num == out['nit'][k]
                      and opt.opt_running_times == out['runs'][k])
     print(f'unseen problems vs scipy: {agree}/{B} identical (ok flag, attempts, iterations, coefficients <= 1e-4 m)')
-    assert agree >= 0.9 * B
+    assert agree >= 0.97 * B
 
 
 @pytest.mark.parametrize('M', [3, 6, 10])
