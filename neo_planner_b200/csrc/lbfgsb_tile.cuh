@@ -28,6 +28,17 @@
 
 namespace neo {
 
+// Development probe (-DNEO_OPT_TICKS, devtools/README.md): cycles spent in each phase of the optimizer, summed over all
+// tiles by their first lane. Compiled out of the shipped library.
+#ifdef NEO_OPT_TICKS
+__device__ long long g_opt_ticks[64];
+#define OT_BEGIN long long ot_last = clock64()
+#define OT(i) do { const long long ot_now = clock64(); if (T.tl == 0) { atomicAdd((unsigned long long *)&g_opt_ticks[i], (unsigned long long)(ot_now - ot_last)); atomicAdd((unsigned long long *)&g_opt_ticks[32 + (i)], 1ull); } ot_last = clock64(); } while (0)
+#else
+#define OT_BEGIN do { } while (0)
+#define OT(i) do { } while (0)
+#endif
+
 // ---- exactly rounded, never contracted -----------------------------------------------------------------------------
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
@@ -38,6 +49,7 @@ __device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a,
 __device__ __noinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __noinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
 __device__ __noinline__ double nrm2_x87(int n, const double *v) { return x87_nrm2(n, v); }
+__device__ __forceinline__ double xrcp(double a) { return __drcp_rn(a); }          // RN(1 / a), same value as xdiv(1, a)
 __device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 // a / b, correctly rounded, given rb = RN(1 / b): q = RN(a rb), then one fused correction with the exact residual
 // (Markstein's theorem; operands here are in the normal range; checked against the hardware division on 4e8 random pairs)
@@ -61,55 +73,59 @@ struct Dcsrch {
 
 __device__ __forceinline__ double max3(double a, double b, double c) { return fmax(a, fmax(b, c)); }
 
-// theta = 3 (fa - fb) / (sb - sa) + da + db  (every operation rounded on its own, as the host code does)
-__device__ __forceinline__ double cubic_theta(double fa, double fb, double sb, double sa, double da, double db)
-{
-    return xadd(xadd(xdiv(xmul(3.0, xsub(fa, fb)), xsub(sb, sa)), da), db);
-}
-// gamma = s * sqrt((theta/s)^2 - (da/s)(db/s)), optionally clamped at zero under the root
-__device__ __forceinline__ double cubic_gamma(double s, double theta, double da, double db, bool clamp)
-{
-    const double ts = xdiv(theta, s);
-    double rad = xsub(xmul(ts, ts), xmul(xdiv(da, s), xdiv(db, s)));
-    if (clamp) rad = fmax(0.0, rad);
-    return xmul(s, xsqrt(rad));
-}
-
-__device__ __noinline__ void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
+// MINPACK-2 dcstep. Every quotient below is the correctly rounded quotient the host code computes; divisions that
+// share a divisor go through one correctly rounded reciprocal (xdiv_r), x / 2 is written x * 0.5 and dx / |dx| is the
+// sign of dx (all exact identities), so the values are bit-identical to a plain transcription at a third of its latency.
+__device__ __forceinline__ void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
                                     double fp, double dp, bool &brackt, double stpmin, double stpmax)
 {
-    const double sgnd = xmul(dp, xdiv(dx, fabs(dx)));
+    const double sgnd = xmul(dp, dx > 0.0 ? 1.0 : (dx < 0.0 ? -1.0 : __longlong_as_double(0x7ff8000000000000LL)));
     double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+    // the cubic through (a: fa, da) and (b: fb, db): theta = 3 (fa - fb) / (sb - sa) + da + db, with 1 / (sb - sa) given
+    auto cubic_theta = [](double fa, double fb, double den, double rden, double da, double db) {
+        return xadd(xadd(xdiv_r(xmul(3.0, xsub(fa, fb)), den, rden), da), db);
+    };
+    // gamma = s * sqrt((theta/s)^2 - (da/s)(db/s)), optionally clamped at zero under the root
+    auto cubic_gamma = [](double s_, double th, double da, double db, bool clamp) {
+        const double rs = __drcp_rn(s_);
+        const double ts = xdiv_r(th, s_, rs);
+        double rad = xsub(xmul(ts, ts), xmul(xdiv_r(da, s_, rs), xdiv_r(db, s_, rs)));
+        if (clamp) rad = fmax(0.0, rad);
+        return xmul(s_, __dsqrt_rn(rad));
+    };
     if (fp > fx) {
-        theta = cubic_theta(fx, fp, stp, stx, dx, dp);
+        const double den = xsub(stp, stx), rden = __drcp_rn(den);
+        theta = cubic_theta(fx, fp, den, rden, dx, dp);
         s = max3(fabs(theta), fabs(dx), fabs(dp));
         gamma = cubic_gamma(s, theta, dx, dp, false);
         if (stp < stx) gamma = -gamma;
-        p = xadd(xsub(gamma, dx), theta); q = xadd(xadd(xsub(gamma, dx), gamma), dp); r = xdiv(p, q);
-        stpc = xadd(stx, xmul(r, xsub(stp, stx)));
-        stpq = xadd(stx, xmul(xdiv(xdiv(dx, xadd(xdiv(xsub(fx, fp), xsub(stp, stx)), dx)), 2.0), xsub(stp, stx)));
-        if (fabs(xsub(stpc, stx)) < fabs(xsub(stpq, stx))) stpf = stpc; else stpf = xadd(stpc, xdiv(xsub(stpq, stpc), 2.0));
+        p = xadd(xsub(gamma, dx), theta); q = xadd(xadd(xsub(gamma, dx), gamma), dp); r = __ddiv_rn(p, q);
+        stpc = xadd(stx, xmul(r, den));
+        stpq = xadd(stx, xmul(xmul(__ddiv_rn(dx, xadd(xdiv_r(xsub(fx, fp), den, rden), dx)), 0.5), den));
+        if (fabs(xsub(stpc, stx)) < fabs(xsub(stpq, stx))) stpf = stpc; else stpf = xadd(stpc, xmul(xsub(stpq, stpc), 0.5));
         brackt = true;
     } else if (sgnd < 0.0) {
-        theta = cubic_theta(fx, fp, stp, stx, dx, dp);
+        const double den = xsub(stp, stx), rden = __drcp_rn(den);
+        theta = cubic_theta(fx, fp, den, rden, dx, dp);
         s = max3(fabs(theta), fabs(dx), fabs(dp));
         gamma = cubic_gamma(s, theta, dx, dp, false);
         if (stp > stx) gamma = -gamma;
-        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dx); r = xdiv(p, q);
+        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dx); r = __ddiv_rn(p, q);
         stpc = xadd(stp, xmul(r, xsub(stx, stp)));
-        stpq = xadd(stp, xmul(xdiv(dp, xsub(dp, dx)), xsub(stx, stp)));
+        stpq = xadd(stp, xmul(__ddiv_rn(dp, xsub(dp, dx)), xsub(stx, stp)));
         if (fabs(xsub(stpc, stp)) > fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
         brackt = true;
     } else if (fabs(dp) < fabs(dx)) {
-        theta = cubic_theta(fx, fp, stp, stx, dx, dp);
+        const double den = xsub(stp, stx), rden = __drcp_rn(den);
+        theta = cubic_theta(fx, fp, den, rden, dx, dp);
         s = max3(fabs(theta), fabs(dx), fabs(dp));
         gamma = cubic_gamma(s, theta, dx, dp, true);
         if (stp > stx) gamma = -gamma;
-        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(gamma, xsub(dx, dp)), gamma); r = xdiv(p, q);
+        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(gamma, xsub(dx, dp)), gamma); r = __ddiv_rn(p, q);
         if (r < 0.0 && gamma != 0.0) stpc = xadd(stp, xmul(r, xsub(stx, stp)));
         else if (stp > stx) stpc = stpmax;
         else stpc = stpmin;
-        stpq = xadd(stp, xmul(xdiv(dp, xsub(dp, dx)), xsub(stx, stp)));
+        stpq = xadd(stp, xmul(__ddiv_rn(dp, xsub(dp, dx)), xsub(stx, stp)));
         if (brackt) {
             if (fabs(xsub(stpc, stp)) < fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
             if (stp > stx) stpf = fmin(xadd(stp, xmul(0.66, xsub(sty, stp))), stpf);
@@ -120,11 +136,12 @@ __device__ __noinline__ void dcstep(double &stx, double &fx, double &dx, double 
         }
     } else {
         if (brackt) {
-            theta = cubic_theta(fp, fy, sty, stp, dy, dp);
+            const double den = xsub(sty, stp), rden = __drcp_rn(den);
+            theta = cubic_theta(fp, fy, den, rden, dy, dp);
             s = max3(fabs(theta), fabs(dy), fabs(dp));
             gamma = cubic_gamma(s, theta, dy, dp, false);
             if (stp > sty) gamma = -gamma;
-            p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dy); r = xdiv(p, q);
+            p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dy); r = __ddiv_rn(p, q);
             stpc = xadd(stp, xmul(r, xsub(sty, stp)));
             stpf = stpc;
         } else if (stp > stx) stpf = stpmax;
@@ -141,13 +158,13 @@ __device__ __noinline__ void dcstep(double &stx, double &fx, double &dx, double 
 __device__ __forceinline__ void dcsrch_start(Dcsrch &S, double stp, double f, double g)
 {
     S.brackt = false; S.stage = 1; S.finit = f; S.ginit = g; S.gtest = xmul(LS_FTOL, g);
-    S.width = LS_STPMAX - LS_STPMIN; S.width1 = xdiv(S.width, 0.5);
+    S.width = LS_STPMAX - LS_STPMIN; S.width1 = xmul(S.width, 2.0);
     S.stx = 0.0; S.fx = f; S.gx = g; S.sty = 0.0; S.fy = f; S.gy = g;
     S.stmin = 0.0; S.stmax = xadd(stp, xmul(4.0, stp));
 }
 
 // 0 = evaluate at stp, 1 = CONVERGENCE, 2 = WARNING
-__device__ __noinline__ int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
+__device__ __forceinline__ int dcsrch_step(Dcsrch &S, double &stp, double f, double g)
 {
     const double ftest = xadd(S.finit, xmul(stp, S.gtest));
     int task = 0;
@@ -210,39 +227,49 @@ __device__ __noinline__ double loop_dot(int n, const double *a, const double *b)
 __device__ __forceinline__ int wn_col(int j) { return j * (j + 1) / 2; }
 
 // dpotrf (OpenBLAS potf2_U) on the n x n diagonal block starting at row/column o. false: not positive definite.
-// rd[o + j] receives 1 / u_jj (used again by the triangular solves)
+// rd[o + j] receives 1 / u_jj (used again by the triangular solves). Per column: the pivot a_jj - ddot(...) and the row
+// sums of this lane's elements are independent chains (issued together); only the final scaling waits for the root.
 __device__ __noinline__ bool lb_potf2(int tl, int TL, unsigned mask, double *wn, double *rd, int o, int n)
 {
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         double *cj = wn + wn_col(o + j) + o;                         // cj[k] = element (o + k, o + j)
-        double ajj = xsub(cj[j], blas_ddot(j, cj, cj));
-        if (!(ajj > 0.0)) return false;                               // same value in every lane of the tile
-        ajj = xsqrt(ajj);
-        __syncwarp(mask);
-        const double r = xdiv(1.0, ajj);
-        if (tl == 0) { cj[j] = ajj; rd[o + j] = r; }
-        if (j < n - 1) {
-            const int m1 = j & ~3, k3 = j - m1;
+        double dot = 0.0;                                             // ddot, j < 16: fused multiply-adds in index order
 #pragma unroll 1
-            for (int i = j + 1 + tl; i < n; i += TL) {
-                double *ci = wn + wn_col(o + i) + o;                 // ci[k] = element (o + k, o + i)
-                double v = ci[j];
+        for (int k = 0; k < j; k++) dot = xfma(cj[k], cj[k], dot);
+        const int m1 = j & ~3, k3 = j - m1;
+        double v[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = j + 1 + tl + q * TL;
+            v[q] = 0.0;
+            if (i < n) {
+                const double *ci = wn + wn_col(o + i) + o;           // ci[k] = element (o + k, o + i)
+                double t = ci[j];
                 if (m1) {                                             // dgemv_t kernel: four rows at a time in four lanes
-                    double acc[4];
-#pragma unroll
-                    for (int l = 0; l < 4; l++) acc[l] = xmul(ci[l], cj[l]);
+                    double a0 = xmul(ci[0], cj[0]), a1 = xmul(ci[1], cj[1]), a2 = xmul(ci[2], cj[2]), a3 = xmul(ci[3], cj[3]);
                     if (m1 == 8) {
-#pragma unroll
-                        for (int l = 0; l < 4; l++) acc[l] = xadd(acc[l], xmul(ci[4 + l], cj[4 + l]));
+                        a0 = xadd(a0, xmul(ci[4], cj[4])); a1 = xadd(a1, xmul(ci[5], cj[5]));
+                        a2 = xadd(a2, xmul(ci[6], cj[6])); a3 = xadd(a3, xmul(ci[7], cj[7]));
                     }
-                    v = xsub(v, xadd(xadd(acc[0], acc[2]), xadd(acc[1], acc[3])));
+                    t = xsub(t, xadd(xadd(a0, a2), xadd(a1, a3)));
                 }
-                if (k3 == 1) v = xfma(ci[m1], -cj[m1], v);
-                else if (k3 == 2) v = xadd(v, xfma(ci[m1], -cj[m1], xmul(ci[m1 + 1], -cj[m1 + 1])));
-                else if (k3 == 3) v = xadd(v, xfma(ci[m1 + 2], -cj[m1 + 2], xfma(ci[m1], -cj[m1], xmul(ci[m1 + 1], -cj[m1 + 1]))));
-                ci[j] = xmul(v, r);
+                if (k3 == 1) t = xfma(ci[m1], -cj[m1], t);
+                else if (k3 == 2) t = xadd(t, xfma(ci[m1], -cj[m1], xmul(ci[m1 + 1], -cj[m1 + 1])));
+                else if (k3 == 3) t = xadd(t, xfma(ci[m1 + 2], -cj[m1 + 2], xfma(ci[m1], -cj[m1], xmul(ci[m1 + 1], -cj[m1 + 1]))));
+                v[q] = t;
             }
+        }
+        double ajj = xsub(cj[j], dot);
+        if (!(ajj > 0.0)) return false;                               // same value in every lane of the tile
+        ajj = __dsqrt_rn(ajj);
+        const double r = __drcp_rn(ajj);
+        __syncwarp(mask);
+        if (tl == 0) { cj[j] = ajj; rd[o + j] = r; }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = j + 1 + tl + q * TL;
+            if (i < n) wn[wn_col(o + i) + o + j] = xmul(v[q], r);
         }
         __syncwarp(mask);
     }
@@ -261,6 +288,7 @@ __device__ __forceinline__ int lb_slot(const LbMem &L, int k) { const int s = L.
 template <int TL>
 __device__ __forceinline__ void lb_update(const Tile<TL> &T, const TileMem &m, int n, LbMem &L, double s, double y, double rr, double dr)
 {
+    OT_BEGIN;
     L.iupdat++;
     if (L.iupdat <= HIST) L.col = L.iupdat;
     else L.head = L.head + 1 == HIST ? 0 : L.head + 1;                // the oldest pair's slot is reused
@@ -282,6 +310,7 @@ __device__ __forceinline__ void lb_update(const Tile<TL> &T, const TileMem &m, i
         }
     }
     T.sync();
+    OT(2);
 }
 
 // formk: assemble the middle matrix and factor it. false: a Cholesky factorisation failed (scipy drops the memory).
@@ -289,7 +318,8 @@ template <int TL>
 __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, const LbMem &L)
 {
     const int col = L.col;
-    const double theta = L.theta, rtheta = xdiv(1.0, theta);
+    OT_BEGIN;
+    const double theta = L.theta, rtheta = xrcp(theta);
     double *wn = m.wn, *rd = m.wn + wn_col(LBW) + LBW;
 #pragma unroll 1
     for (int iy = T.tl; iy < col; iy += TL) {
@@ -313,7 +343,9 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
     }
     // NOTE the transposition: formk fills wn(jy, is) = R_z(iy, jy) for jy >= iy -- column `is`, rows jy: c2[jy] above.
     T.sync();
+    OT(3);
     if (!lb_potf2(T.tl, TL, T.mask, wn, rd, 0, col)) return false;
+    OT(4);
     if (col == 1) {                                                    // one right-hand side: trsv, a true division
         if (T.tl == 0) wn[wn_col(1)] = xdiv_r(wn[wn_col(1)], wn[0], rd[0]);
     } else {                                                           // blocked trsm kernel: 8, 4, 2, 1 rows
@@ -344,6 +376,7 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
         }
     }
     T.sync();
+    OT(5);
 #pragma unroll 1
     for (int js = col; js < 2 * col; js++) {
         const double *cjs = wn + wn_col(js);
@@ -352,7 +385,10 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
             wn[wn_col(js) + is] = xadd(wn[wn_col(js) + is], blas_ddot(col, wn + wn_col(is), cjs));
     }
     T.sync();
-    return lb_potf2(T.tl, TL, T.mask, wn, rd, col, col);
+    OT(6);
+    const bool pd = lb_potf2(T.tl, TL, T.mask, wn, rd, col, col);
+    OT(7);
+    return pd;
 }
 
 // subsm with r = -g: returns the lane-owned component of the subspace step
@@ -360,7 +396,8 @@ template <int TL>
 __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, int n, const LbMem &L, double g)
 {
     const int col = L.col, m2 = 2 * col;
-    const double theta = L.theta, rtheta = xdiv(1.0, theta);
+    OT_BEGIN;
+    const double theta = L.theta, rtheta = xrcp(theta);
     double *wn = m.wn, *wv = m.wn + wn_col(LBW), *rd = wv + LBW;
     double d = -g;
     if (T.tl < n) m.dv[T.tl] = d;
@@ -369,6 +406,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
     for (int e = T.tl; e < m2; e += TL)
         wv[e] = e < col ? loop_dot(n, m.wy + lb_slot(L, e) * n, m.dv) : xmul(theta, loop_dot(n, m.ws + lb_slot(L, e - col) * n, m.dv));
     T.sync();
+    OT(8);
     // trsv, transposed: b_i = (b_i - ddot(i, u(0:i, i), b)) / u_ii. Every row's inner product is a chain of fused
     // multiply-adds in index order, so all rows advance together as each b_k becomes final.
     {
@@ -402,6 +440,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
         }
     }
     T.sync();
+    OT(9);
 #pragma unroll 1
     for (int i = T.tl; i < col; i += TL) wv[i] = -wv[i];
     T.sync();
@@ -416,6 +455,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
         for (int k = T.tl; k < i; k += TL) wv[k] = xfma(t, ui[k], wv[k]);
         T.sync();
     }
+    OT(10);
     if (T.tl < n) {
 #pragma unroll 1
         for (int jy = 0; jy < col; jy++) {
@@ -425,6 +465,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
         d = xmul(d, rtheta);
     }
     T.sync();
+    OT(11);
     return d;
 }
 
@@ -483,13 +524,16 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
     const double tol = (ftol / epsmch) * epsmch;
     const int maxls = 20, maxiter = 15000, maxfun = 15000;
     bool new_dir;
+    OT_BEGIN;
     if (o.first) {
         o.first = false;
         if (T.dmax(mine ? fabs(o.g) : 0.0) <= pgtol) { o.status = 1; return; }
         new_dir = true;
     } else {
         o.gd = opt_gd(T, m, n, o.g, o.d);
-        if (dcsrch_step(o.ls, o.stp, o.f, o.gd) == 0) new_dir = false;            // FG: another trial point
+        const int ls_task = dcsrch_step(o.ls, o.stp, o.f, o.gd);
+        OT(0);
+        if (ls_task == 0) new_dir = false;                                       // FG: another trial point
         else {
             // ---- the line search accepted the last evaluated point -------------------------------------------------
             o.nit++;
@@ -505,8 +549,10 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             T.sync();
             if (mine) m.dv[T.tl] = y;
             T.sync();
+            OT(12);
             const double nr = nrm2_x87(n, m.dv);
             const double rr = xmul(nr, nr);
+            OT(1);
             double dr, ddum, s;
             if (o.stp == 1.0) { dr = xsub(o.gd, o.gdold); ddum = -o.gdold; s = o.d; }
             else { dr = xmul(xsub(o.gd, o.gdold), o.stp); s = xmul(o.d, o.stp); ddum = xmul(-o.gdold, o.stp); }
@@ -517,6 +563,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
     for (;;) {      // (re)start a line search; loops only when a failed search drops the memory
         if (new_dir) {
             // ---- direction: Cauchy point x - g with an empty memory (theta = 1), else the subspace step; d = z - x ---
+            OT(15);
             if (o.L.col > 0 && !lb_factor(T, m, o.L)) { o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0; }
             if (o.L.col == 0) o.z = xsub(o.x, o.g);
             else o.z = xadd(o.x, lb_step(T, m, n, o.L, o.g));
@@ -525,7 +572,9 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             T.sync();
             if (mine) m.dv[T.tl] = o.d;
             T.sync();
+            OT(13);
             const double dnorm = nrm2_x87(n, m.dv);
+            OT(1);
             o.stp = (o.nit == 0) ? fmin(xdiv(1.0, dnorm), LS_STPMAX) : 1.0;
             o.t = o.x; o.r = o.g; o.fold = o.f;
             o.gd = opt_gd(T, m, n, o.g, o.d);
@@ -533,6 +582,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             o.ifun = 0;
             if (o.gd >= 0.0) o.ifun = maxls + 1;                                // not a descent direction: fail
             else dcsrch_start(o.ls, o.stp, o.f, o.gd);
+            OT(14);
         }
         o.ifun++;
         if (o.ifun - 1 < maxls) break;                                          // evaluate the trial point

@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
             if (!opt_same_point(T, o, n)) {
                 // ---- the evaluation site: f, g at x --------------------------------------------------------------
                 EvalOut ev;
+                OT_BEGIN;
                 eval_fg<MODE, TL>(T, P, map, m, M, o.x, true, ev);
+                OT(16);
                 o.ns += ev.ns; o.nv += ev.nv; o.nc += ev.nc;
                 if (a.tr_x && o.nfev < a.trace_cap) {
                     const size_t k = (size_t)tid * a.trace_cap + o.nfev;
@@ -1419,6 +1421,18 @@ extern "C" int neo_test_exp_dev(neo_handle *h, int n, const double *x, double *y
     CK(cudaStreamSynchronize(h->stream));
     return NEO_OK;
 }
+
+#ifdef NEO_OPT_TICKS
+// development probe: read and clear the optimizer's phase counters (cycles [0..32), calls [32..64))
+extern "C" int neo_test_opt_ticks(long long *out)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_opt_ticks, sizeof(long long) * 64);
+    long long z[64] = {0};
+    cudaMemcpyToSymbol(g_opt_ticks, z, sizeof(z));
+    return NEO_OK;
+}
+#endif
 
 extern "C" int neo_test_exp_host(int n, const double *x, double *y)
 {

@@ -50,21 +50,23 @@ def unpack_records(rec: np.ndarray, M: int):
     return out
 
 
-def gather_records(local_rec: np.ndarray, local_idx: np.ndarray, total: int, device=None):
+def gather_records(local_rec: np.ndarray, local_idx: np.ndarray, total: int, device=None, counts=None, offset: int = 0):
     """All-gather the per-rank records into global problem order on every rank. Ranks may own different counts:
-    records are padded to the maximum count (one collective of fixed size, then the padding is dropped)."""
+    records are padded to the maximum count (one collective of fixed size, then the padding is dropped).
+    counts: per-rank record counts if the caller knows them (saves the object gather); offset is added to local_idx."""
     import torch
     import torch.distributed as dist
     ws = dist.get_world_size()
     width = local_rec.shape[1]
-    counts = [None] * ws
-    dist.all_gather_object(counts, int(local_rec.shape[0]))
+    if counts is None:
+        counts = [None] * ws
+        dist.all_gather_object(counts, int(local_rec.shape[0]))
     cap = max(counts)
     dev = torch.device('cpu') if device is None else device
     buf = torch.zeros((cap, width + 1), dtype=torch.float64, device=dev)
     if local_rec.shape[0]:
         buf[:local_rec.shape[0], :width] = torch.from_numpy(local_rec).to(dev)
-        buf[:local_rec.shape[0], width] = torch.from_numpy(np.asarray(local_idx, dtype=np.float64)).to(dev)
+        buf[:local_rec.shape[0], width] = torch.from_numpy(np.asarray(local_idx, dtype=np.float64) + float(offset)).to(dev)
     allbuf = torch.zeros((ws * cap, width + 1), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(allbuf, buf)
     allbuf = allbuf.cpu().numpy().reshape(ws, cap, width + 1)
