@@ -377,12 +377,13 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
     }
     T.sync();
     OT(5);
+    // (2,2) block: every entry (is <= js) gets its own inner product over the first col rows -- one lane each
 #pragma unroll 1
-    for (int js = col; js < 2 * col; js++) {
-        const double *cjs = wn + wn_col(js);
-#pragma unroll 1
-        for (int is = col + T.tl; is <= js; is += TL)
-            wn[wn_col(js) + is] = xadd(wn[wn_col(js) + is], blas_ddot(col, wn + wn_col(is), cjs));
+    for (int e = T.tl; e < col * (col + 1) / 2; e += TL) {
+        int jj = 0;
+        while ((jj + 1) * (jj + 2) / 2 <= e) jj++;                    // column (relative), row = e - jj (jj + 1) / 2
+        const int ii = e - jj * (jj + 1) / 2, js = col + jj, is = col + ii;
+        wn[wn_col(js) + is] = xadd(wn[wn_col(js) + is], blas_ddot(col, wn + wn_col(is), wn + wn_col(js)));
     }
     T.sync();
     OT(6);

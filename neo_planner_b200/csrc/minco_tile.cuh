@@ -127,18 +127,37 @@ struct TileMem {
 // staging rows of the sample loop's partial sums: one block of 15 rows per piece when all pieces are parked before the
 // owners add them (by-piece schedule, latency-optimised), one block otherwise (see eval_fg)
 __host__ __device__ inline int red_doubles(int M, int TL, bool one_block) { return (M > 4 || one_block) ? 15 * (TL + 1) : 15 * (TL + 1) * M; }
-__host__ __device__ inline int shared_region_doubles(int M, int TL, bool one_block)
+
+// Layout of a tile's slice. Shared memory is what limits the number of problems in flight per SM, so regions whose
+// lifetimes do not overlap share storage:
+//   [ht]                                     head / tail states: live for the whole problem
+//   [A: ts ex iT gT P U blk c gC e0 nsd gout pc]   evaluation scratch, rewritten by every evaluation
+//   [B: red  |  r lam h Gs]                  the sample loop's partial sums, then (same storage) the adjoint's vectors;
+//                                            r is also used by the node solve, before the sample loop starts
+//   A and B together hold the factored middle matrix wn + wv + 1/diagonal while a search direction is computed
+//   (no evaluation is in flight then)
+//   [ws wy yr rzd dr] [gv dv]                optimizer state: live across evaluations
+//   [lw nsprev asg]                          cached lane assignment of the all-pieces schedule (M > 4)
+__host__ __device__ inline int scratch_a_doubles(int M)
 {
-    const int r = red_doubles(M, TL, one_block);
-    return r > WN_DOUBLES ? r : WN_DOUBLES;
+    const int n = 3 * M - 2, M1 = M + 1;
+    return M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * (M - 1) + 12 * M + 12 * M + 2 * M + 2 * M + n + 2 * M;
+}
+__host__ __device__ inline int scratch_b_doubles(int M, int TL, bool one_block)
+{
+    const int M1 = M + 1, adj = 4 * M1 + 4 * M1 + 12 * M + 10 * M1, red = red_doubles(M, TL, one_block);
+    return red > adj ? red : adj;
+}
+__host__ __device__ inline int scratch_doubles(int M, int TL, bool one_block)
+{
+    const int ab = scratch_a_doubles(M) + scratch_b_doubles(M, TL, one_block);
+    return ab > WN_DOUBLES ? ab : WN_DOUBLES;
 }
 
 __host__ __device__ inline int tile_mem_doubles(int M, int TL = 32, bool one_block = false)
 {
-    const int n = 3 * M - 2, M1 = M + 1;
-    int tot = M + M + 5 * M + M + 2 * M1 + 4 * M1 + 12 * M1 + 4 * M1 + 4 * M1 + 12 * M + 12 * M + 12 * M + 10 * M1 +
-              2 * M + 2 * M + n + 12 + 2 * M + 2 * HIST * n + HIST * HIST + 2 * HIST + 2 * n +
-              shared_region_doubles(M, TL, one_block) + (M > 4 ? 2 * M + M + 32 : 0);
+    const int n = 3 * M - 2;
+    int tot = 12 + scratch_doubles(M, TL, one_block) + 2 * HIST * n + HIST * HIST + 2 * HIST + 2 * n + (M > 4 ? 2 * M + M + 32 : 0);
     return (tot + 1) & ~1;
 }
 
@@ -146,24 +165,28 @@ __device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block
 {
     const int n = 3 * M - 2, M1 = M + 1;
     TileMem m;
+    m.ht = base; base += 12;
+    double *const scratch = base;
+    m.wn = scratch;
     m.ts = base; base += M;
     m.ex = base; base += M;
     m.iT = base; base += 5 * M;
     m.gT = base; base += M;
     m.P = base; base += 2 * M1;
     m.U = base; base += 4 * M1;
-    m.blk = base; base += 12 * M1;
-    m.r = base; base += 4 * M1;
-    m.lam = base; base += 4 * M1;
+    m.blk = base - 12; base += 12 * (M - 1);        // indexed by interior node 1..M-1
     m.c = base; base += 12 * M;
     m.gC = base; base += 12 * M;
-    m.h = base; base += 12 * M;
-    m.Gs = base; base += 10 * M1;
     m.e0 = base; base += 2 * M;
     m.nsd = base; base += 2 * M;
     m.gout = base; base += n;
-    m.ht = base; base += 12;
     m.pc = base; base += 2 * M;
+    m.red = base;                                   // B: partial sums of the sample loop ...
+    m.r = base;                                     // ... or the adjoint's vectors
+    m.lam = m.r + 4 * M1;
+    m.h = m.lam + 4 * M1;
+    m.Gs = m.h + 12 * M;
+    base = scratch + scratch_doubles(M, TL, one_block);
     m.ws = base; base += HIST * n;
     m.wy = base; base += HIST * n;
     m.yr = base; base += HIST * HIST;
@@ -171,7 +194,6 @@ __device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block
     m.dr = base; base += HIST;
     m.gv = base; base += n;
     m.dv = base; base += n;
-    m.red = base; m.wn = base; base += shared_region_doubles(M, TL, one_block);
     m.lw = base; m.nsprev = base + 2 * M; m.asg = base + 3 * M;      // only carved for M > 4 (see tile_mem_doubles)
     return m;
 }

@@ -7,7 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -24,8 +26,11 @@ using namespace neo;
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
 #ifndef NEO_TILE_MIN_PROBLEMS
-#define NEO_TILE_MIN_PROBLEMS 8192   // batch size from which short trajectories (M <= 4) run several problems per warp
-                                     // (measured break-even on B200: 4 k problems 5.2 vs 4.5 ms, 16 k 11.4 vs 12.9 ms)
+#define NEO_TILE_MIN_PROBLEMS 32768  // batch size from which short trajectories (M <= 4) run several problems per warp
+                                     // (measured on B200: 16 k problems 11.1 vs 11.2 ms, 65 k 38.8 vs 43.2 ms)
+#endif
+#ifndef NEO_HOST_THREADS
+#define NEO_HOST_THREADS 8            // neo_optimize: host threads that assemble inputs / scatter results of a large batch
 #endif
 #ifndef NEO_PACKED_MIN_PER_SM
 #define NEO_PACKED_MIN_PER_SM 324    // problems x pieces per SM from which the 3-CTAs-per-SM instantiation is launched
@@ -1030,6 +1035,28 @@ struct TraceHost {
     int32_t *status, *len;
 };
 
+// Splits [0, count) over up to NEO_HOST_THREADS host threads (large batches only) and runs fn(begin, end) on each part.
+template <typename F>
+static void parallel_ranges(size_t count, F fn)
+{
+    const size_t min_per = 4096;
+    size_t nt = count / min_per;
+    if (nt > NEO_HOST_THREADS) nt = NEO_HOST_THREADS;
+    if (nt <= 1) { fn((size_t)0, count); return; }
+    std::vector<std::thread> th;
+    const size_t per = (count + nt - 1) / nt;
+    for (size_t t = 1; t < nt; t++) {
+        const size_t b0 = t * per, b1 = b0 + per < count ? b0 + per : count;
+        if (b0 < b1) th.emplace_back([=] { fn(b0, b1); });
+    }
+    fn((size_t)0, per < count ? per : count);
+    for (auto &t : th) t.join();
+}
+
+// Host-buffer entry: inputs are assembled in ONE pinned staging buffer that mirrors the device layout
+// (x0 = [q0, map_T2tau(ts0)], EP:207-211), moved with ONE H2D copy; results come back with ONE D2H copy and are
+// scattered into the caller's arrays. For large batches both host passes run on several threads (at 65,536 problems
+// they move 50 MB and take 196,608 logarithms -- a quarter of the kernel's time on one thread).
 static int optimize_host(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
                          const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
                          int max_attempts, neo_result *out, const TraceHost *trace)
@@ -1048,14 +1075,12 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     CK(cudaSetDevice(h->device));
     const size_t n = 3 * M - 2, nq = 2 * (M - 1), N2 = 12 * M, b = B, A1 = max_attempts - 1;
 
-    // One pinned staging buffer mirrors the device layout: [inputs | outputs]. Inputs are assembled in place
-    // (x0 = [q0, map_T2tau(ts0)], EP:207-211), moved with ONE H2D copy; results come back with ONE D2H copy.
     struct Lay {
         size_t x0, head, tail, st0, ids, rq, rtau, in_end, x, ts, coeffs, costs, status, ok, attempt, nit, runs, nfev, work, end;
     } L;
     {
-        Carver c{nullptr};
-        auto off = [&](size_t bytes) { c.off = (c.off + 255) & ~(size_t)255; size_t o = c.off; c.off += bytes; return o; };
+        size_t o = 0;
+        auto off = [&](size_t bytes) { o = (o + 255) & ~(size_t)255; const size_t at = o; o += bytes; return at; };
         L.x0 = off(8 * b * n); L.head = off(8 * b * 6); L.tail = off(8 * b * 6); L.st0 = off(4 * b); L.ids = off(4 * b);
         L.rq = off(8 * (b * A1 * nq + 1)); L.rtau = off(8 * NEO_MAX_PIECES); L.in_end = off(0);
         L.x = off(8 * b * n); L.ts = off(8 * b * M); L.coeffs = off(8 * b * N2); L.costs = off(8 * b * 4);
@@ -1068,26 +1093,32 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
 
     double *hx0 = (double *)(hbase + L.x0);
     int32_t *hst = (int32_t *)(hbase + L.st0);
-    bool any_bad = false;
-    for (size_t i = 0; i < b; i++) {
-        memcpy(&hx0[i * n], q0 + i * nq, sizeof(double) * nq);
-        int st = 0;
-        for (int k = 0; k < M; k++) {
-            double t = 0.0;
-            const int s1 = T2tau_one(&h->cfg, ts0[i * M + k], &t);
-            hx0[i * n + nq + k] = s1 ? 0.0 : t;
-            if (s1) st = s1;
+    const neo_config cfg = h->cfg;
+    std::atomic<int> any_bad_flag{0};
+    parallel_ranges(b, [&](size_t i0, size_t i1) {
+        bool bad = false;
+        for (size_t i = i0; i < i1; i++) {
+            memcpy(&hx0[i * n], q0 + i * nq, sizeof(double) * nq);
+            int s0 = 0;
+            for (int k = 0; k < M; k++) {
+                double t = 0.0;
+                const int s1 = T2tau_one(&cfg, ts0[i * M + k], &t);
+                hx0[i * n + nq + k] = s1 ? 0.0 : t;
+                if (s1) s0 = s1;
+            }
+            hst[i] = s0;
+            bad = bad || s0;
         }
-        hst[i] = st;
-        any_bad = any_bad || st;
-    }
+        memcpy(hbase + L.head + 48 * i0, head + i0 * 6, 48 * (i1 - i0));
+        memcpy(hbase + L.tail + 48 * i0, tail + i0 * 6, 48 * (i1 - i0));
+        if (map_ids) memcpy(hbase + L.ids + 4 * i0, map_ids + i0, 4 * (i1 - i0));
+        if (A1) memcpy(hbase + L.rq + 8 * i0 * A1 * nq, retry_q + i0 * A1 * nq, 8 * (i1 - i0) * A1 * nq);
+        if (bad) any_bad_flag.store(1);
+    });
+    const bool any_bad = any_bad_flag.load() != 0;
     double *rtau = (double *)(hbase + L.rtau);
     int rstatus = 0;
     if (A1) for (int k = 0; k < M; k++) { rtau[k] = 0.0; const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
-    memcpy(hbase + L.head, head, 8 * b * 6);
-    memcpy(hbase + L.tail, tail, 8 * b * 6);
-    if (map_ids) memcpy(hbase + L.ids, map_ids, 4 * b);
-    if (A1) memcpy(hbase + L.rq, retry_q, 8 * b * A1 * nq);
 
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(dbase, hbase, L.in_end, cudaMemcpyHostToDevice, st));
@@ -1132,17 +1163,20 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     CK(cudaMemcpyAsync(hbase + L.x, dbase + L.x, L.end - L.x, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    memcpy(out->x, hbase + L.x, 8 * b * n);
-    memcpy(out->ts, hbase + L.ts, 8 * b * M);
-    memcpy(out->coeffs, hbase + L.coeffs, 8 * b * N2);
-    memcpy(out->costs, hbase + L.costs, 8 * b * 4);
-    memcpy(out->status, hbase + L.status, 4 * b);
-    memcpy(out->ok, hbase + L.ok, 4 * b);
-    memcpy(out->attempt, hbase + L.attempt, 4 * b);
-    memcpy(out->nit, hbase + L.nit, 4 * b);
-    memcpy(out->runs, hbase + L.runs, 4 * b);
-    memcpy(out->nfev, hbase + L.nfev, 4 * b);
-    if (out->work) memcpy(out->work, hbase + L.work, 8 * b * 4);
+    parallel_ranges(b, [&](size_t i0, size_t i1) {
+        const size_t c = i1 - i0;
+        memcpy(out->x + i0 * n, hbase + L.x + 8 * i0 * n, 8 * c * n);
+        memcpy(out->ts + i0 * M, hbase + L.ts + 8 * i0 * M, 8 * c * M);
+        memcpy(out->coeffs + i0 * N2, hbase + L.coeffs + 8 * i0 * N2, 8 * c * N2);
+        memcpy(out->costs + i0 * 4, hbase + L.costs + 32 * i0, 32 * c);
+        memcpy(out->status + i0, hbase + L.status + 4 * i0, 4 * c);
+        memcpy(out->ok + i0, hbase + L.ok + 4 * i0, 4 * c);
+        memcpy(out->attempt + i0, hbase + L.attempt + 4 * i0, 4 * c);
+        memcpy(out->nit + i0, hbase + L.nit + 4 * i0, 4 * c);
+        memcpy(out->runs + i0, hbase + L.runs + 4 * i0, 4 * c);
+        memcpy(out->nfev + i0, hbase + L.nfev + 4 * i0, 4 * c);
+        if (out->work) memcpy(out->work + i0 * 4, hbase + L.work + 32 * i0, 32 * c);
+    });
     return NEO_OK;
 }
 
