@@ -1,8 +1,9 @@
 """Body/world frame transforms and the network I/O layout of the reference (record_planner.py:13-72,
 nn_planner.py:104-134), batched in NumPy. The reference uses pyquaternion objects (`.rotate`, `.inverse`,
-`.rotation_matrix`); pyquaternion is not installed here, so the unit-quaternion algebra is restated (w, x, y, z order)
-and checked against scipy.spatial.transform.Rotation in tests/test_host_logic.py -- parity with pyquaternion itself
-is unpinned (rounding-level only: both evaluate q v q*)."""
+`.rotation_matrix`); here the unit-quaternion algebra is restated on arrays (w, x, y, z order). Pinned in
+tests/test_host_logic.py against tests/golden/nn_io.npz -- the outputs of the reference's own form_nn_input /
+form_nn_output / get_wpts_world, run unmodified by oracle/gen_golden.py with a stand-in for pyquaternion (not
+installed here) -- to 1e-13, and against scipy.spatial.transform.Rotation."""
 from __future__ import annotations
 
 import numpy as np
@@ -82,3 +83,24 @@ def wpts_world(attitude, global_pos, net_out, M=3):
     local = net_out[:, :3 * (M - 1)].reshape(B, M - 1, 3)
     world = rotate(np.asarray(attitude)[:, None, :], local) + np.asarray(global_pos, dtype=np.float64)[:, None, :]
     return np.ascontiguousarray(np.transpose(world[:, :, :2], (0, 2, 1))), net_out[:, 3 * (M - 1):].copy()
+
+
+def quat_array(attitude):
+    """(w, x, y, z) from what the reference passes as `drone_state.attitude`: a pyquaternion.Quaternion (`.q` /
+    `.elements`), or already an array."""
+    for attr in ('q', 'elements'):
+        v = getattr(attitude, attr, None)
+        if v is not None:
+            return np.asarray(v, dtype=np.float64)
+    return np.asarray(attitude, dtype=np.float64)
+
+
+def clamp_durations(ts, T_min, T_max, margin=1e-3):
+    """SURVEY.md §8d (config 3): network durations outside (T_min, T_max) make map_T2tau raise on entry (EP:209), so the
+    reference throws the whole guess away and retries from a noisy straight line. clamp_durations moves them just
+    inside the interval instead (and reports which samples it touched) so that the predicted WAYPOINTS still warm-start
+    the optimizer. Returns (ts_clamped, touched (B,) bool)."""
+    ts = np.asarray(ts, dtype=np.float64)
+    lo, hi = T_min + margin * (T_max - T_min), T_max - margin * (T_max - T_min)
+    out = np.clip(np.where(np.isfinite(ts), ts, lo), lo, hi)
+    return out, np.any(out != ts, axis=-1)

@@ -360,8 +360,146 @@ def gen_geo(name):
           'geo plans ok', sum(1 for v in P_ok if v == 1), '/', sum(1 for v in P_ok if v >= 0))
 
 
+def stub_modules(*names):
+    """Registers empty stand-in modules (with a module spec, torch's import scans ask for it) for packages the reference
+    imports but never uses on the paths exercised here."""
+    import importlib.machinery
+    import types
+    for nm in names:
+        if nm not in sys.modules:
+            m = types.ModuleType(nm)
+            m.__spec__ = importlib.machinery.ModuleSpec(nm, None)
+            sys.modules[nm] = m
+    return [sys.modules[nm] for nm in names]
+
+
+class Quaternion:
+    """Stand-in for pyquaternion.Quaternion (not installed here; the reference's record_planner / nn_planner use
+    `.rotate`, `.inverse`, `.rotation_matrix` of it). Same algebra as pyquaternion 0.9: products through the 4x4 left
+    matrix, rotation as q v q*, rotation matrix as the lower-right 3x3 of Q(q) Qbar(q)^T, each after normalisation."""
+
+    def __init__(self, w=1.0, x=0.0, y=0.0, z=0.0, array=None):
+        self.q = np.array([w, x, y, z], dtype=float) if array is None else np.array(array, dtype=float)
+
+    def _normalised(self):
+        n = np.sqrt(np.dot(self.q, self.q))
+        return Quaternion(array=self.q / n) if abs(1.0 - n) > 1e-14 else self
+
+    def _q_matrix(self):
+        w, x, y, z = self.q
+        return np.array([[w, -x, -y, -z], [x, w, -z, y], [y, z, w, -x], [z, -y, x, w]])
+
+    def _q_bar_matrix(self):
+        w, x, y, z = self.q
+        return np.array([[w, -x, -y, -z], [x, w, z, -y], [y, -z, w, x], [z, y, -x, w]])
+
+    def __mul__(self, other):
+        return Quaternion(array=np.dot(self._q_matrix(), other.q))
+
+    @property
+    def conjugate(self):
+        return Quaternion(array=self.q * np.array([1.0, -1.0, -1.0, -1.0]))
+
+    @property
+    def inverse(self):
+        return Quaternion(array=self.conjugate.q / np.dot(self.q, self.q))
+
+    def rotate(self, v):
+        u = self._normalised()
+        return (u * Quaternion(array=np.concatenate(([0.0], np.asarray(v, dtype=float)))) * u.conjugate).q[1:]
+
+    @property
+    def rotation_matrix(self):
+        u = self._normalised()
+        return np.dot(u._q_matrix(), u._q_bar_matrix().conj().transpose())[1:][:, 1:]
+
+
+def gen_nn_io(name):
+    """§8f rank 3 / a24: form_nn_input, form_nn_output (record_planner.py:13-72) and NNPlanner.get_wpts_world
+    (nn_planner.py:123-134) of the unmodified reference on seeded drone states. pyquaternion and onnxruntime are not
+    installed: the Quaternion stand-in above and empty onnxruntime / torchinfo / onnx / matplotlib modules are registered
+    before the imports (nn_planner is only imported for the get_wpts_world method, no session is created)."""
+    import types
+    from types import SimpleNamespace as NS
+    stub_modules('onnxruntime', 'torchinfo', 'onnx', 'matplotlib', 'matplotlib.pyplot', 'pyquaternion')
+    sys.modules['torchinfo'].summary = lambda *a, **k: None
+    sys.modules['pyquaternion'].Quaternion = Quaternion
+    sys.path.insert(0, REF)                                   # nn_planner imports nn_trainer.nn_trainer as a package
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    from record_planner import form_nn_input, form_nn_output  # noqa: E402  (reference)
+    from nn_planner import NNPlanner  # noqa: E402  (reference)
+    rng = np.random.default_rng(31)
+    B = 12
+    des_z = 2.0
+    quat = rng.normal(size=(B, 4)); quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    quat[0] = [1, 0, 0, 0]; quat[1] = [np.cos(0.3), 0, 0, np.sin(0.3)]
+    local_vel = rng.normal(0, 1, (B, 3)); gpos = rng.uniform(-5, 25, (B, 3)); gvel = rng.normal(0, 1, (B, 3))
+    ipos = gpos + rng.normal(0, 0.5, (B, 3)); ivel = gvel + rng.normal(0, 0.2, (B, 3))
+    target = np.stack([ipos[:, :2] + rng.uniform(3, 6, (B, 2)), rng.normal(0, 1, (B, 2))], axis=1)
+    depth = rng.uniform(0.2, 12.0, (B, 48, 64)).astype(np.float32)
+    int_wpts = rng.uniform(-5, 25, (B, 2, 2))
+    net_local = rng.normal(0, 2, (B, 3, 2))
+    d_norm = []; motion = []; out_local = []; world = []
+    for k in range(B):
+        q = Quaternion(*quat[k])
+        ds = NS(local_vel=local_vel[k], attitude=q, global_pos=gpos[k], global_vel=gvel[k])
+        st = NS(global_pos=ipos[k], global_vel=ivel[k])
+        dn, mi = form_nn_input(depth[k], ds, des_z, st, target[k])
+        d_norm.append(dn); motion.append(mi)
+        out_local.append(form_nn_output(ds, des_z, int_wpts[k]))
+        fake = NS(drone_state=ds, nn_output_D=3, M=3)
+        world.append(NNPlanner.get_wpts_world(fake, net_local[k]))
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, des_pos_z=des_z, quat=quat, local_vel=local_vel, global_pos=gpos,
+                        global_vel=gvel, init_pos=ipos, init_vel=ivel, target=target, depth=depth, int_wpts=int_wpts,
+                        net_local=net_local, depth_norm=np.array(d_norm), motion=np.array(motion),
+                        int_wpts_local=np.array(out_local), wpts_world=np.array(world))
+    print(name, 'samples', B)
+
+
+def gen_nets(name):
+    """a24 / §8f rank 4: the reference's two PlannerNet classes (nn_trainer.py:109-155 MLP heads, nn_trainer_conv.py:108-160
+    Conv1d heads) instantiated unmodified -- torchvision's resnet18 is told not to download weights -- filled with
+    oracle/net_weights.fill_deterministic and run in fp32 on oracle/net_weights.sample_input."""
+    import types
+    import torch
+    import torchvision.models as tvm
+    from oracle import net_weights
+    stub_modules('onnxruntime', 'torchinfo', 'onnx', 'matplotlib', 'matplotlib.pyplot')
+    sys.modules['torchinfo'].summary = lambda *a, **k: None
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    orig = tvm.resnet18
+    tvm.resnet18 = lambda weights=None, **kw: orig(weights=None, **kw)       # no network here: skip the ImageNet download
+    import importlib.util
+
+    def load(fname):                                     # the unmodified reference file, loaded by path
+        spec = importlib.util.spec_from_file_location('ref_' + fname[:-3], os.path.join(REF, 'nn_trainer', fname))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    try:
+        ref_mlp = load('nn_trainer.py')
+        ref_conv = load('nn_trainer_conv.py')
+        x = torch.from_numpy(net_weights.sample_input())
+        out = {}
+        for tag, mod in (('mlp', ref_mlp), ('conv', ref_conv)):
+            net = mod.PlannerNet().eval()
+            net_weights.fill_deterministic(net)
+            with torch.no_grad():
+                y = net(x)
+            out[tag + '_out'] = y.reshape(x.shape[0], -1).numpy()
+            out[tag + '_sig'] = np.array(net_weights.signature(net))
+    finally:
+        tvm.resnet18 = orig
+    np.savez_compressed(os.path.join(OUT, name), versions=VERS, torch_version=np.array(torch.__version__), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:      # python oracle/gen_golden.py nn_io nets  -> only these fixtures
+        for which in sys.argv[1:]:
+            {'nn_io': lambda: gen_nn_io('nn_io.npz'), 'nets': lambda: gen_nets('nets.npz')}[which]()
+        sys.exit(0)
     gen_esdf()
     gen_eval(3, 24, 'eval_M3.npz')
     gen_eval(10, 8, 'eval_M10.npz')
@@ -371,3 +509,5 @@ if __name__ == '__main__':
     gen_batch_plan(16, 'batch_plan_M3.npz')
     gen_errors('errors.npz')
     gen_geo('geo_M3.npz')
+    gen_nn_io('nn_io.npz')
+    gen_nets('nets.npz')

@@ -70,3 +70,56 @@ def test_learned_initializer_feeds_optimizer():
     warm = bp.warm_start_plan(head[good], tail[good], expert['x'][good][:, :4].reshape(-1, 2, 2), expert['ts'][good],
                               rng=np.random.default_rng(3))
     assert warm['nit'].mean() < 0.5 * expert['nit'][good].mean()
+
+
+def test_single_problem_dropins_have_the_reference_signatures(tmp_path):
+    """NeoPlanner.enhanced_traj_plan (neo_planner.py:42-51), NNPlanner.nn_traj_plan (nn_planner.py:70-82) and
+    RecordPlanner.record_traj_plan (record_planner.py:136-150) with the reference's argument lists: map object, one
+    depth frame, drone_state / plan_init_state objects (attributes local_vel, attitude, global_pos, global_vel),
+    target_state (2,2). The single-problem classes must agree with the batch classes on the same inputs."""
+    import os
+    from types import SimpleNamespace as NS
+    import torch
+    from neo_planner_b200.esdf import ESDF
+    from neo_planner_b200.initializer import NeoBatchPlanner, NeoPlanner, PlannerNetConv
+    B = 4
+    w, head, tail, att, gp, gv, lv, depth, init_pos, init_vel = scene(B, seed=5)
+    cfg = YamlConfig(); cfg.des_pos_z = 2.0
+    e = ESDF(); e.occupancy_map_cb(w.occupancy_msg())
+    torch.manual_seed(42)
+    net = PlannerNetConv()
+    bp = BatchPlanner(cfg); bp.set_map(w)
+    batch = NeoBatchPlanner(bp, des_pos_z=2.0, net=net, device='cuda', clamp_ts=True)
+    np.random.seed(9)
+    res = batch.enhanced_traj_plan(depth, lv, att, gp, gv, init_pos, init_vel, tail)
+    assert res['nn_ts_outside_bounds'].shape == (B,)
+    neo = NeoPlanner(cfg, net=net, clamp_ts=True)
+    np.random.seed(9)
+    for k in range(B):
+        ds = NS(local_vel=lv[k], attitude=NS(q=att[k]), global_pos=gp[k], global_vel=gv[k])      # .q like pyquaternion
+        st = NS(global_pos=init_pos[k], global_vel=init_vel[k])
+        try:
+            neo.enhanced_traj_plan(e, depth[k], ds, st, tail[k])
+            ok = 1
+        except Exception:
+            ok = 0
+        assert neo.nn_planner.int_wpts.shape == (2, 2) and neo.nn_planner.ts.shape == (3,)
+        assert np.allclose(neo.nn_planner.int_wpts, res['nn_int_wpts'][k], atol=2e-2)         # bf16 network, batch of 1 vs 4
+        assert ok == res['ok'][k]
+        if ok:
+            assert neo.coeffs.shape == (18, 2) and np.abs(neo.coeffs[0] - head[k, 0]).max() < 1e-9
+    # RecordPlanner: one row + one PNG per call
+    from neo_planner_b200.record import RecordPlanner, TABLE_HEADER
+    rp = RecordPlanner(cfg, out_dir=str(tmp_path / 'training_data'))
+    wrote = 0
+    for k in range(B):
+        ds = NS(local_vel=lv[k], attitude=att[k], global_pos=gp[k], global_vel=gv[k])
+        st = NS(global_pos=init_pos[k], global_vel=init_vel[k])
+        try:
+            rp.record_traj_plan(e, depth[k], ds, st, tail[k])
+            wrote += 1
+            assert rp.int_wpts.shape == (2, 2)
+        except Exception:
+            pass
+    back = pd.read_csv(rp.csv_path)
+    assert list(back.columns) == TABLE_HEADER and len(back) == wrote == len(os.listdir(rp.img_path)) and wrote >= 2

@@ -234,3 +234,65 @@ def test_T2tau_host_matches_python_math_with_repeats():
     bad = np.array([np.nan, 2.5]); tau = np.zeros(2); st = np.zeros(2, np.int32)      # NaN durations are rejected up front
     lib.load().neo_T2tau(C.byref(cfg), 2, lib.ptr(bad), lib.ptr(tau), lib.ptr(st))
     assert st.tolist() == [lib.ST_DOMAIN, 0]
+
+
+# ---- pins generated from the unmodified reference (oracle/gen_golden.py nn_io nets) --------------------------------
+def test_nn_io_against_reference_functions(golden):
+    """frames.py vs the reference's own form_nn_input / form_nn_output (record_planner.py:13-72) and
+    NNPlanner.get_wpts_world (nn_planner.py:123-134), run unmodified on seeded drone states when the fixture was made
+    (with a pyquaternion stand-in: q v q* through the 4x4 product matrices, like pyquaternion 0.9)."""
+    from neo_planner_b200 import frames
+    g = golden('nn_io.npz')
+    dn, mi = frames.form_nn_input(g['depth'], g['local_vel'], g['quat'], g['global_pos'], g['global_vel'], float(g['des_pos_z']),
+                                  g['init_pos'], g['init_vel'], g['target'])
+    assert dn.dtype == np.uint8 and np.array_equal(dn, g['depth_norm'])                # truncation to uint8: exact
+    assert mi.shape == g['motion'].shape == (12, 24)
+    assert np.max(np.abs(mi - g['motion'])) <= 1e-13 * max(1.0, np.max(np.abs(g['motion'])))
+    loc = frames.form_nn_output(g['quat'], g['global_pos'], float(g['des_pos_z']), g['int_wpts'])
+    assert np.max(np.abs(loc - g['int_wpts_local'])) <= 1e-13 * np.max(np.abs(g['int_wpts_local']))
+    # network output layout (nn_planner.py:104-105): [wpt1 xyz, wpt2 xyz, ts1..3] -> (3, 2) body-frame columns
+    net_out = np.concatenate([np.transpose(g['net_local'], (0, 2, 1)).reshape(12, 6), np.ones((12, 3))], axis=1)
+    world, ts = frames.wpts_world(g['quat'], g['global_pos'], net_out)
+    assert np.max(np.abs(world - g['wpts_world'][:, :2, :])) <= 1e-13 * np.max(np.abs(g['wpts_world']))
+    assert np.array_equal(ts, np.ones((12, 3)))
+
+
+@pytest.mark.parametrize('tag', ['mlp', 'conv'])
+def test_initializer_networks_match_the_reference_classes(golden, tag):
+    """Structural parity of initializer.PlannerNet / PlannerNetConv with nn_trainer.py:109-155 / nn_trainer_conv.py:108-160:
+    identical state_dict keys and shapes, and -- with the same deterministic weights (oracle/net_weights.py) on the same
+    seeded input -- the fp32 outputs the reference classes produced when the fixture was generated."""
+    import torch
+    from neo_planner_b200 import initializer
+    from oracle import net_weights
+    g = golden('nets.npz')
+    net = (initializer.PlannerNet() if tag == 'mlp' else initializer.PlannerNetConv()).eval()
+    assert net_weights.signature(net) == [str(s) for s in g[tag + '_sig']]
+    net_weights.fill_deterministic(net)
+    with torch.no_grad():
+        y = net(torch.from_numpy(net_weights.sample_input())).reshape(2, -1).numpy()
+    ref = g[tag + '_out']
+    assert y.shape == ref.shape == (2, 9)
+    assert np.max(np.abs(y - ref)) <= 1e-4 * max(1.0, np.max(np.abs(ref))), np.max(np.abs(y - ref))
+
+
+def test_record_ids_are_unique_across_calls_and_ranks():
+    """two batches recorded within the same few milliseconds must not share ids (the id names the depth PNG)."""
+    import datetime
+    from neo_planner_b200 import record
+    now = datetime.datetime(2026, 1, 2, 3, 4, 5, 678000)
+    a = record.make_ids(1024, now=now)
+    b = record.make_ids(1024, now=now + datetime.timedelta(milliseconds=100))
+    assert len(set(a)) == 1024 and not set(a) & set(b)
+    assert all(i[0] == 't' and i[1:].isdigit() for i in a)
+    r0 = record.make_ids(64, now=now, rank=0, world_size=4)
+    r3 = record.make_ids(64, now=now, rank=3, world_size=4)
+    assert not set(r0) & set(r3) and not (set(r0) | set(r3)) & (set(a) | set(b))
+
+
+def test_clamp_durations_flags_out_of_range_predictions():
+    from neo_planner_b200 import frames
+    ts = np.array([[1.0, 2.0, 3.0], [0.2, 2.0, 9.0], [np.nan, 1.0, 1.0]])
+    out, touched = frames.clamp_durations(ts, 0.5, 5.0)
+    assert touched.tolist() == [False, True, True] and np.array_equal(out[0], ts[0])
+    assert ((out > 0.5) & (out < 5.0)).all()
