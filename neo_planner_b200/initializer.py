@@ -192,9 +192,10 @@ class NeoPlanner(MinJerkPlanner):
     when a predicted duration falls outside (T_min, T_max) (frames.clamp_durations); False is the reference: map_T2tau
     raises and the first retry starts from a noisy straight line (EP:197-200)."""
 
-    def __init__(self, planner_config, device: int = 0, net=None, clamp_ts=False):
+    def __init__(self, planner_config, device: int = 0, net=None, clamp_ts=False, dtype=torch.bfloat16):
         super().__init__(planner_config, device)
-        self.nn_planner = NNPlanner(planner_config.des_pos_z, net=net, device=f'cuda:{device}' if torch.cuda.is_available() else 'cpu')
+        self.nn_planner = NNPlanner(planner_config.des_pos_z, net=net, dtype=dtype,
+                                    device=f'cuda:{device}' if torch.cuda.is_available() else 'cpu')
         self.clamp_ts = clamp_ts
 
     def enhanced_traj_plan(self, map, depth_img, drone_state, plan_init_state, target_state):
