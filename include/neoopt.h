@@ -87,6 +87,11 @@ int neo_set_map_esdf(neo_handle *h, int slot, int H, int W, double res, double o
  * Bit-exact with scipy.ndimage.distance_transform_edt + numpy.gradient. */
 int neo_set_map_occupancy(neo_handle *h, int slot, int H, int W, double res, double ox, double oy,
                           const int8_t *occ);
+/* The same for K maps of one shape (H, W, res) in one call: slots (K) distinct map slots, ox / oy (K) origins, occ
+ * (K, H, W). One synchronisation at the end instead of one per map (the 256 generated worlds of the data-generation
+ * sweep, BASELINE.json configs[3]). */
+int neo_set_maps_occupancy(neo_handle *h, int K, const int32_t *slots, int H, int W, double res, const double *ox,
+                           const double *oy, const int8_t *occ);
 /* Map build from a point cloud / voxel-centre list (the step before ESDF.occupancy_map_cb, done by the external
  * octomap_server in the reference: map_server_global.launch:17-31): xyz (n,3) float32 as stored in a .pcd; a cell
  * (row = floor((y-oy)/res), col = floor((x-ox)/res)) is occupied iff a point with z_min <= z <= z_max falls into it;

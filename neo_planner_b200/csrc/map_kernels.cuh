@@ -26,24 +26,35 @@ __global__ void k_points_to_occ(const float *__restrict__ xyz, int n, double z_m
     if (fr >= 0.0 && fr < (double)H && fc >= 0.0 && fc < (double)W) occ[(size_t)(int)fr * W + (int)fc] = 100;
 }
 
-// pass 1: one thread per row; g[r][c] = squared distance to the nearest occupied cell of row r (EDT_INF if none)
+// pass 1: one warp per row; g[r][c] = squared distance to the nearest occupied cell of row r (EDT_INF if none).
+// The row is walked in 32-cell chunks, forwards (nearest occupied cell at or left of c) and backwards (at or right of
+// c); inside a chunk every lane finds its neighbour in the ballot word of the chunk, the carry is one integer.
 __global__ void k_edt_rows(const int8_t *__restrict__ occ, int H, int W, int *__restrict__ g, int *__restrict__ any)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= H) return;
     const int8_t *o = occ + (size_t)r * W;
     int *row = g + (size_t)r * W;
-    int last = -1, seen = 0;
-    for (int c = 0; c < W; c++) {
-        if (o[c] == 100) { last = c; seen = 1; }            // ESDF:23: only 100 is occupied, unknown(-1) is free
-        row[c] = last < 0 ? EDT_INF : (c - last) * (c - last);
+    int last = -1;
+    for (int c0 = 0; c0 < W; c0 += 32) {
+        const int c = c0 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, c < W && o[c] == 100);   // ESDF:23: only 100 is occupied, unknown(-1) is free
+        const unsigned mine = m & (0xffffffffu >> (31 - lane));                // occupied cells at or left of this lane
+        const int left = mine ? c0 + 31 - __clz(mine) : last;
+        if (c < W) row[c] = left < 0 ? EDT_INF : (c - left) * (c - left);
+        if (m) last = c0 + 31 - __clz(m);
     }
+    if (lane == 0 && last >= 0) atomicOr(any, 1);
     last = -1;
-    for (int c = W - 1; c >= 0; c--) {
-        if (o[c] == 100) last = c;
-        if (last >= 0) { const int d = (last - c) * (last - c); if (d < row[c]) row[c] = d; }
+    for (int c0 = ((W - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+        const int c = c0 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, c < W && o[c] == 100);
+        const unsigned mine = m & (0xffffffffu << lane);                       // occupied cells at or right of this lane
+        const int right = mine ? c0 + __ffs(mine) - 1 : last;
+        if (c < W && right >= 0) { const int d = (right - c) * (right - c); if (d < row[c]) row[c] = d; }
+        if (m) last = c0 + __ffs(m) - 1;
     }
-    if (seen) atomicOr(any, 1);
 }
 
 // pass 2: one thread per cell; exact min over rows rr of (r-rr)^2 + g[rr][c], scanning outward from r and

@@ -379,6 +379,7 @@ struct neo_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     neo_config cfg;
     std::vector<MapSlot> slots;
+    std::vector<MapView> views;      // host copies of the published views (sources of the async uploads)
     MapView *d_maps = nullptr;
     unsigned int *d_counter = nullptr;
     std::vector<DevBuf> bufs;        // reusable device staging buffers for the host-pointer entry points
@@ -476,7 +477,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
         return NEO_ERR_NO_DEVICE;
     }
     neo_handle *h = new neo_handle();
-    h->device = device; h->cfg = *cfg; h->slots.resize(max_maps);
+    h->device = device; h->cfg = *cfg; h->slots.resize(max_maps); h->views.resize(max_maps);
     if (const char *e = getenv("NEO_TILE")) { const int t = atoi(e); h->tile = (t == 8 || t == 16 || t == 32) ? t : 0; }
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
@@ -546,7 +547,7 @@ static int slot_prepare(neo_handle *h, int slot, int H, int W, double res, doubl
     return NEO_OK;
 }
 
-static int slot_publish(neo_handle *h, int slot)
+static int slot_publish(neo_handle *h, int slot, bool sync = true)
 {
     MapSlot &s = h->slots[slot];
     MapView v;
@@ -565,8 +566,9 @@ static int slot_publish(neo_handle *h, int slot)
     h->launches++;
     CK(cudaGetLastError());
     v.blocked = s.blocked;
-    CK(cudaMemcpyAsync(h->d_maps + slot, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    h->views[slot] = v;                 // pageable source of an async copy: must outlive the call
+    CK(cudaMemcpyAsync(h->d_maps + slot, &h->views[slot], sizeof(v), cudaMemcpyHostToDevice, h->stream));
+    if (sync) CK(cudaStreamSynchronize(h->stream));
     return NEO_OK;
 }
 
@@ -593,7 +595,8 @@ extern "C" int neo_set_map_esdf(neo_handle *h, int slot, int H, int W, double re
 }
 
 // occupancy (device, int8) -> exact EDT -> cells; d_occ lives in staging buffer 0 (offset 0)
-static int build_from_occ(neo_handle *h, int slot, int H, int W, double res, char *base, size_t off_g, size_t off_any, size_t off_e)
+static int build_from_occ(neo_handle *h, int slot, int H, int W, double res, char *base, size_t off_g, size_t off_any, size_t off_e,
+                          bool sync = true)
 {
     const int8_t *d_occ = (const int8_t *)base;
     int *d_g = (int *)(base + off_g), *d_any = (int *)(base + off_any);
@@ -604,13 +607,13 @@ static int build_from_occ(neo_handle *h, int slot, int H, int W, double res, cha
     if (!s.occ) { CK(cudaMalloc(&s.occ, n)); s.occ_cap = n; }
     CK(cudaMemcpyAsync(s.occ, d_occ, n, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemsetAsync(d_any, 0, sizeof(int), h->stream));
-    k_edt_rows<<<(H + 63) / 64, 64, 0, h->stream>>>(d_occ, H, W, d_g, d_any);
+    k_edt_rows<<<(H + 7) / 8, 256, 0, h->stream>>>(d_occ, H, W, d_g, d_any);                 // one warp per row
     dim3 grid((W + 127) / 128, H);
     k_edt_cols<<<grid, 128, 0, h->stream>>>(d_g, H, W, d_any, res, d_e);
     k_pack_cells<<<grid, 128, 0, h->stream>>>(d_e, nullptr, nullptr, H, W, s.cells, nullptr, nullptr);
     h->launches += 3;
     CK(cudaGetLastError());
-    return slot_publish(h, slot);
+    return slot_publish(h, slot, sync);
 }
 
 struct OccLayout { size_t off_g, off_any, off_e, total; };
@@ -640,6 +643,42 @@ extern "C" int neo_set_map_occupancy(neo_handle *h, int slot, int H, int W, doub
     if ((rc = dev_buf(h, 0, L.total, (void **)&base))) return rc;
     CK(cudaMemcpyAsync(base, occ, n, cudaMemcpyHostToDevice, h->stream));
     return build_from_occ(h, slot, H, W, res, base, L.off_g, L.off_any, L.off_e);
+}
+
+// K maps of one shape in one call (the 256 generated worlds of the data-generation sweep): one H2D copy per group of
+// maps, every build enqueued back to back on the handle's stream, ONE synchronisation at the end.
+extern "C" int neo_set_maps_occupancy(neo_handle *h, int K, const int32_t *slots, int H, int W, double res, const double *ox,
+                                      const double *oy, const int8_t *occ)
+{
+    if (!h) return NEO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (K < 0 || !slots || !ox || !oy || !occ) return fail(h, "neo_set_maps_occupancy: invalid argument");
+    if ((long long)H * H + (long long)W * W >= (long long)EDT_INF) return fail(h, "map too large for the int32 EDT");
+    for (int k = 0; k < K; k++) {
+        if (slots[k] < 0 || slots[k] >= (int)h->slots.size()) return fail(h, "map slot out of range");
+        for (int j = 0; j < k; j++) if (slots[j] == slots[k]) return fail(h, "neo_set_maps_occupancy: a slot is named twice");
+    }
+    if (K == 0) return NEO_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)H * W;
+    const OccLayout L = occ_layout(n);
+    const size_t stride = (L.total + 255) & ~(size_t)255;
+    const int group = K < 32 ? K : 32;                        // staging for 32 maps at a time
+    char *base;
+    int rc = dev_buf(h, 0, stride * group, (void **)&base);
+    if (rc) return rc;
+    for (int k0 = 0; k0 < K; k0 += group) {
+        const int kn = K - k0 < group ? K - k0 : group;
+        if (k0) CK(cudaStreamSynchronize(h->stream));          // the staging block is reused by the next group
+        for (int k = 0; k < kn; k++) {
+            if ((rc = slot_prepare(h, slots[k0 + k], H, W, res, ox[k0 + k], oy[k0 + k]))) return rc;
+            CK(cudaMemcpyAsync(base + stride * k, occ + n * (size_t)(k0 + k), n, cudaMemcpyHostToDevice, h->stream));
+        }
+        for (int k = 0; k < kn; k++)
+            if ((rc = build_from_occ(h, slots[k0 + k], H, W, res, base + stride * k, L.off_g, L.off_any, L.off_e, false))) return rc;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return NEO_OK;
 }
 
 extern "C" int neo_set_map_points(neo_handle *h, int slot, int n_points, const float *xyz, double z_min, double z_max,

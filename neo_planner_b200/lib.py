@@ -44,7 +44,7 @@ class Result(C.Structure):
 
 
 EXPORTS = ['neo_create', 'neo_destroy', 'neo_set_config', 'neo_last_error', 'neo_device_info', 'neo_set_map_esdf',
-           'neo_set_map_occupancy', 'neo_set_map_points', 'neo_get_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
+           'neo_set_map_occupancy', 'neo_set_maps_occupancy', 'neo_set_map_points', 'neo_get_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
            'neo_optimize_dev', 'neo_optimize_trace', 'neo_T2tau', 'neo_get_coeffs', 'neo_sample', 'neo_last_kernel_ms', 'neo_fp64_peak',
            'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host', 'neo_astar', 'neo_astar_dev']
 
@@ -68,6 +68,7 @@ def load():
         lib.neo_device_info.argtypes = [V, V, V, V, V, I]
         lib.neo_set_map_esdf.argtypes = [V, I, I, I, D, D, D, V, V, V]
         lib.neo_set_map_occupancy.argtypes = [V, I, I, I, D, D, D, V]
+        lib.neo_set_maps_occupancy.argtypes = [V, I, V, I, I, D, V, V, V]
         lib.neo_get_map.argtypes = [V, I, V, V, V]
         lib.neo_set_map_points.argtypes = [V, I, I, V, D, D, I, I, D, D, D]
         lib.neo_get_occupancy.argtypes = [V, I, V]
@@ -161,6 +162,13 @@ class Handle:
     def set_map_occupancy(self, slot, H, W, res, ox, oy, occ):
         occ = np.ascontiguousarray(np.asarray(occ).reshape(H, W), dtype=np.int8)
         self._ck(self.lib.neo_set_map_occupancy(self.h, slot, H, W, res, ox, oy, ptr(occ)))
+
+    def set_maps_occupancy(self, slots, H, W, res, ox, oy, occ):
+        """K maps of one shape in one call: slots (K), ox / oy (K), occ (K, H, W)."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32); K = slots.size
+        occ = np.ascontiguousarray(np.asarray(occ).reshape(K, H, W), dtype=np.int8)
+        ox = f64(np.broadcast_to(np.asarray(ox, dtype=np.float64), (K,))); oy = f64(np.broadcast_to(np.asarray(oy, dtype=np.float64), (K,)))
+        self._ck(self.lib.neo_set_maps_occupancy(self.h, K, ptr(slots), H, W, float(res), ptr(ox), ptr(oy), ptr(occ)))
 
     def set_map_points(self, slot, xyz, z_min, z_max, H, W, res, ox, oy):
         xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)

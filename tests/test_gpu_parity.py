@@ -367,3 +367,27 @@ def test_eval_extreme_time_allocations(M, world0):
     gerr = np.max(np.abs(out['grad'] - grad), axis=1) / np.max(np.abs(grad), axis=1)
     print(f'M={M}: extreme T: worst rel cost err {np.max(np.abs(f_dev - f_ref) / np.abs(f_ref)):.2e}, worst rel grad err {gerr.max():.2e}')
     assert gerr.max() <= 1e-6
+
+
+def test_batched_map_build_equals_single_builds():
+    """neo_set_maps_occupancy (K maps, one synchronisation) builds exactly what K neo_set_map_occupancy calls build, and
+    both equal the CPU checker's scipy-exact EDT (ESDF:23-33)."""
+    import time
+    K = 12
+    worlds = [make_world(40 + k) for k in range(K)]
+    w0 = worlds[0]
+    h1 = lib.Handle(YamlConfig(), 0, K); h2 = lib.Handle(YamlConfig(), 0, K)
+    t0 = time.perf_counter()
+    for k, w in enumerate(worlds):
+        h1.set_map_occupancy(k, w.H, w.W, w.res, w.ox, w.oy, w.occ)
+    t1 = time.perf_counter()
+    h2.set_maps_occupancy(np.arange(K)[::-1].copy(), w0.H, w0.W, w0.res, [w.ox for w in worlds][::-1], [w.oy for w in worlds][::-1],
+                          np.stack([np.asarray(w.occ).reshape(w.H, w.W) for w in worlds])[::-1].copy())
+    t2 = time.perf_counter()
+    for k, w in enumerate(worlds):
+        a = h1.get_map(k, w.H, w.W); b = h2.get_map(k, w.H, w.W)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        m = c_oracle.OracleMap.from_world(w)
+        assert np.array_equal(b[0], m.esdf) and np.array_equal(b[1], m.gx) and np.array_equal(b[2], m.gy)
+    print(f'{K} maps: {1e3 * (t1 - t0):.2f} ms one by one, {1e3 * (t2 - t1):.2f} ms in one call')
