@@ -75,57 +75,57 @@ __device__ __forceinline__ double max3(double a, double b, double c) { return fm
 
 // MINPACK-2 dcstep. Every quotient below is the correctly rounded quotient the host code computes; divisions that
 // share a divisor go through one correctly rounded reciprocal (xdiv_r), x / 2 is written x * 0.5 and dx / |dx| is the
-// sign of dx (all exact identities), so the values are bit-identical to a plain transcription at a third of its latency.
+// sign of dx (all exact identities), so the values are bit-identical to a plain transcription.
+// The four cases of the routine differ in which points feed the cubic and in a few signs; the expensive part (one
+// cubic: two reciprocals, a square root, two divisions) is written ONCE on case-selected operands, so that the tiles
+// of a warp that are in different cases still execute it together instead of one case after the other.
 __device__ __forceinline__ void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
-                                    double fp, double dp, bool &brackt, double stpmin, double stpmax)
+                                       double fp, double dp, bool &brackt, double stpmin, double stpmax)
 {
     const double sgnd = xmul(dp, dx > 0.0 ? 1.0 : (dx < 0.0 ? -1.0 : __longlong_as_double(0x7ff8000000000000LL)));
-    double stpf, stpc, stpq, theta, s, gamma, p, q, r;
-    // the cubic through (a: fa, da) and (b: fb, db): theta = 3 (fa - fb) / (sb - sa) + da + db, with 1 / (sb - sa) given
-    auto cubic_theta = [](double fa, double fb, double den, double rden, double da, double db) {
-        return xadd(xadd(xdiv_r(xmul(3.0, xsub(fa, fb)), den, rden), da), db);
-    };
-    // gamma = s * sqrt((theta/s)^2 - (da/s)(db/s)), optionally clamped at zero under the root
-    auto cubic_gamma = [](double s_, double th, double da, double db, bool clamp) {
-        const double rs = __drcp_rn(s_);
-        const double ts = xdiv_r(th, s_, rs);
-        double rad = xsub(xmul(ts, ts), xmul(xdiv_r(da, s_, rs), xdiv_r(db, s_, rs)));
-        if (clamp) rad = fmax(0.0, rad);
-        return xmul(s_, __dsqrt_rn(rad));
-    };
-    if (fp > fx) {
-        const double den = xsub(stp, stx), rden = __drcp_rn(den);
-        theta = cubic_theta(fx, fp, den, rden, dx, dp);
-        s = max3(fabs(theta), fabs(dx), fabs(dp));
-        gamma = cubic_gamma(s, theta, dx, dp, false);
-        if (stp < stx) gamma = -gamma;
-        p = xadd(xsub(gamma, dx), theta); q = xadd(xadd(xsub(gamma, dx), gamma), dp); r = __ddiv_rn(p, q);
+    const int kase = fp > fx ? 1 : (sgnd < 0.0 ? 2 : (fabs(dp) < fabs(dx) ? 3 : 4));
+    const bool cubic = kase < 4 || brackt;
+    // the cubic through (a: fa, da) and (stp: fb, dp): theta = 3 (fa - fb) / den + da + dp
+    const double fa = kase < 4 ? fx : fp, fb = kase < 4 ? fp : fy, da = kase < 4 ? dx : dy;
+    const double den = kase < 4 ? xsub(stp, stx) : xsub(sty, stp);
+    double theta = 0.0, gamma = 0.0, rden = 0.0;
+    if (cubic) {
+        rden = __drcp_rn(den);
+        theta = xadd(xadd(xdiv_r(xmul(3.0, xsub(fa, fb)), den, rden), da), dp);
+        const double s = max3(fabs(theta), fabs(da), fabs(dp));
+        const double rs = __drcp_rn(s);
+        const double ts = xdiv_r(theta, s, rs);
+        double rad = xsub(xmul(ts, ts), xmul(xdiv_r(da, s, rs), xdiv_r(dp, s, rs)));
+        if (kase == 3) rad = fmax(0.0, rad);
+        gamma = xmul(s, __dsqrt_rn(rad));
+        const bool flip = kase == 1 ? stp < stx : (kase == 4 ? stp > sty : stp > stx);
+        if (flip) gamma = -gamma;
+    }
+    // r = p / q
+    const double g1 = xsub(gamma, kase == 1 ? dx : dp);
+    const double p = xadd(g1, theta);
+    const double q = kase == 3 ? xadd(xadd(gamma, xsub(dx, dp)), gamma) : xadd(xadd(g1, gamma), kase == 1 ? dp : (kase == 2 ? dx : dy));
+    const double r = cubic ? __ddiv_rn(p, q) : 0.0;
+    // the secant / quadratic step: case 1 dx / ((fx - fp) / den + dx) / 2, cases 2 and 3 dp / (dp - dx)
+    const double qn = kase == 1 ? dx : dp;
+    const double qd = kase == 1 ? xadd(xdiv_r(xsub(fx, fp), den, rden), dx) : xsub(dp, dx);
+    const double qq = kase < 4 ? __ddiv_rn(qn, qd) : 0.0;
+    double stpf, stpc, stpq;
+    if (kase == 1) {
         stpc = xadd(stx, xmul(r, den));
-        stpq = xadd(stx, xmul(xmul(__ddiv_rn(dx, xadd(xdiv_r(xsub(fx, fp), den, rden), dx)), 0.5), den));
+        stpq = xadd(stx, xmul(xmul(qq, 0.5), den));
         if (fabs(xsub(stpc, stx)) < fabs(xsub(stpq, stx))) stpf = stpc; else stpf = xadd(stpc, xmul(xsub(stpq, stpc), 0.5));
         brackt = true;
-    } else if (sgnd < 0.0) {
-        const double den = xsub(stp, stx), rden = __drcp_rn(den);
-        theta = cubic_theta(fx, fp, den, rden, dx, dp);
-        s = max3(fabs(theta), fabs(dx), fabs(dp));
-        gamma = cubic_gamma(s, theta, dx, dp, false);
-        if (stp > stx) gamma = -gamma;
-        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dx); r = __ddiv_rn(p, q);
+    } else if (kase == 2) {
         stpc = xadd(stp, xmul(r, xsub(stx, stp)));
-        stpq = xadd(stp, xmul(__ddiv_rn(dp, xsub(dp, dx)), xsub(stx, stp)));
+        stpq = xadd(stp, xmul(qq, xsub(stx, stp)));
         if (fabs(xsub(stpc, stp)) > fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
         brackt = true;
-    } else if (fabs(dp) < fabs(dx)) {
-        const double den = xsub(stp, stx), rden = __drcp_rn(den);
-        theta = cubic_theta(fx, fp, den, rden, dx, dp);
-        s = max3(fabs(theta), fabs(dx), fabs(dp));
-        gamma = cubic_gamma(s, theta, dx, dp, true);
-        if (stp > stx) gamma = -gamma;
-        p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(gamma, xsub(dx, dp)), gamma); r = __ddiv_rn(p, q);
+    } else if (kase == 3) {
         if (r < 0.0 && gamma != 0.0) stpc = xadd(stp, xmul(r, xsub(stx, stp)));
         else if (stp > stx) stpc = stpmax;
         else stpc = stpmin;
-        stpq = xadd(stp, xmul(__ddiv_rn(dp, xsub(dp, dx)), xsub(stx, stp)));
+        stpq = xadd(stp, xmul(qq, xsub(stx, stp)));
         if (brackt) {
             if (fabs(xsub(stpc, stp)) < fabs(xsub(stpq, stp))) stpf = stpc; else stpf = stpq;
             if (stp > stx) stpf = fmin(xadd(stp, xmul(0.66, xsub(sty, stp))), stpf);
@@ -135,16 +135,8 @@ __device__ __forceinline__ void dcstep(double &stx, double &fx, double &dx, doub
             stpf = fmin(stpmax, stpf); stpf = fmax(stpmin, stpf);
         }
     } else {
-        if (brackt) {
-            const double den = xsub(sty, stp), rden = __drcp_rn(den);
-            theta = cubic_theta(fp, fy, den, rden, dy, dp);
-            s = max3(fabs(theta), fabs(dy), fabs(dp));
-            gamma = cubic_gamma(s, theta, dy, dp, false);
-            if (stp > sty) gamma = -gamma;
-            p = xadd(xsub(gamma, dp), theta); q = xadd(xadd(xsub(gamma, dp), gamma), dy); r = __ddiv_rn(p, q);
-            stpc = xadd(stp, xmul(r, xsub(sty, stp)));
-            stpf = stpc;
-        } else if (stp > stx) stpf = stpmax;
+        if (brackt) stpf = xadd(stp, xmul(r, xsub(sty, stp)));
+        else if (stp > stx) stpf = stpmax;
         else stpf = stpmin;
     }
     if (fp > fx) { sty = stp; fy = fp; dy = dp; }
@@ -223,6 +215,29 @@ __device__ __noinline__ double loop_dot(int n, const double *a, const double *b)
     return s;
 }
 
+// the same two inner products for a vector length known at compile time (n = 3M - 2, short trajectories): straight-line
+// code instead of a call and a loop -- identical operations in identical order
+template <int N>
+__device__ __forceinline__ double loop_dot_n(const double *a, const double *b, int n = N)
+{
+    if constexpr (N > 0 && N <= 10) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) s = xadd(s, xmul(a[i], b[i]));
+        return s;
+    } else return loop_dot(n, a, b);
+}
+template <int N>
+__device__ __forceinline__ double blas_ddot_n(const double *a, const double *b, int n = N)
+{
+    if constexpr (N > 0 && N <= 10) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) s = xfma(a[i], b[i], s);
+        return s;
+    } else return blas_ddot(n, a, b);
+}
+
 // packed upper triangle: element (i, j), i <= j
 __device__ __forceinline__ int wn_col(int j) { return j * (j + 1) / 2; }
 
@@ -285,7 +300,7 @@ struct LbMem {
 __device__ __forceinline__ int lb_slot(const LbMem &L, int k) { const int s = L.head + k; return s >= HIST ? s - HIST : s; }
 
 // matupd + the bookkeeping formk does for a new pair: s, y are the lane-owned components (tl < n)
-template <int TL>
+template <int TL, int NC>
 __device__ __forceinline__ void lb_update(const Tile<TL> &T, const TileMem &m, int n, LbMem &L, double s, double y, double rr, double dr)
 {
     OT_BEGIN;
@@ -302,10 +317,10 @@ __device__ __forceinline__ void lb_update(const Tile<TL> &T, const TileMem &m, i
     for (int e = T.tl; e < 2 * col; e += TL) {
         if (e < col) {                                                 // row `col` of Y'Y
             const int sj = lb_slot(L, e);
-            m.yr[slot * HIST + sj] = loop_dot(n, ynew, m.wy + sj * n);
+            m.yr[slot * HIST + sj] = loop_dot_n<NC>(ynew, m.wy + sj * n, n);
         } else {                                                       // column `col` of R_z
             const int si = lb_slot(L, e - col);
-            const double v = loop_dot(n, m.ws + si * n, ynew);
+            const double v = loop_dot_n<NC>(m.ws + si * n, ynew, n);
             if (si == slot) m.rzd[slot] = v; else m.yr[si * HIST + slot] = v;
         }
     }
@@ -393,7 +408,7 @@ __device__ __forceinline__ bool lb_factor(const Tile<TL> &T, const TileMem &m, c
 }
 
 // subsm with r = -g: returns the lane-owned component of the subspace step
-template <int TL>
+template <int TL, int NC>
 __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, int n, const LbMem &L, double g)
 {
     const int col = L.col, m2 = 2 * col;
@@ -405,7 +420,7 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
     T.sync();
 #pragma unroll 1
     for (int e = T.tl; e < m2; e += TL)
-        wv[e] = e < col ? loop_dot(n, m.wy + lb_slot(L, e) * n, m.dv) : xmul(theta, loop_dot(n, m.ws + lb_slot(L, e - col) * n, m.dv));
+        wv[e] = e < col ? loop_dot_n<NC>(m.wy + lb_slot(L, e) * n, m.dv, n) : xmul(theta, loop_dot_n<NC>(m.ws + lb_slot(L, e - col) * n, m.dv, n));
     T.sync();
     OT(8);
     // trsv, transposed: b_i = (b_i - ddot(i, u(0:i, i), b)) / u_ii. Every row's inner product is a chain of fused
@@ -503,20 +518,20 @@ __device__ __forceinline__ bool opt_same_point(const Tile<TL> &T, const OptState
 }
 
 // g . d with the BLAS kernel's summation order (both vectors go through shared memory so that every lane can add them)
-template <int TL>
+template <int TL, int NC>
 __device__ __forceinline__ double opt_gd(const Tile<TL> &T, const TileMem &m, int n, double g, double d)
 {
     T.sync();
     if (T.tl < n) { m.gv[T.tl] = g; m.dv[T.tl] = d; }
     T.sync();
-    return blas_ddot(n, m.gv, m.dv);
+    return blas_ddot_n<NC>(m.gv, m.dv, n);
 }
 
 // Called after every evaluation (or cache hit) with f, g in place: one step of plan_once's minimize() (EP:213-225).
 // Leaves the next trial point in o.x, or sets o.status (>= 0) when minimize() returns.
 // cancel_word/cancel_mask: when (*cancel_word & cancel_mask) becomes non-zero (an earlier attempt of the same problem
 // has been accepted, so this speculative attempt can never be the returned one) the run stops with ST_CANCELLED.
-template <int TL>
+template <int TL, int NC>
 __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m, int n, OptState &o,
                                             const unsigned *cancel_word, unsigned cancel_mask)
 {
@@ -531,7 +546,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
         if (T.dmax(mine ? fabs(o.g) : 0.0) <= pgtol) { o.status = 1; return; }
         new_dir = true;
     } else {
-        o.gd = opt_gd(T, m, n, o.g, o.d);
+        o.gd = opt_gd<TL, NC>(T, m, n, o.g, o.d);
         const int ls_task = dcsrch_step(o.ls, o.stp, o.f, o.gd);
         OT(0);
         if (ls_task == 0) new_dir = false;                                       // FG: another trial point
@@ -557,7 +572,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             double dr, ddum, s;
             if (o.stp == 1.0) { dr = xsub(o.gd, o.gdold); ddum = -o.gdold; s = o.d; }
             else { dr = xmul(xsub(o.gd, o.gdold), o.stp); s = xmul(o.d, o.stp); ddum = xmul(-o.gdold, o.stp); }
-            if (!(dr <= xmul(epsmch, ddum))) lb_update(T, m, n, o.L, s, y, rr, dr);
+            if (!(dr <= xmul(epsmch, ddum))) lb_update<TL, NC>(T, m, n, o.L, s, y, rr, dr);
             new_dir = true;
         }
     }
@@ -567,7 +582,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             OT(15);
             if (o.L.col > 0 && !lb_factor(T, m, o.L)) { o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0; }
             if (o.L.col == 0) o.z = xsub(o.x, o.g);
-            else o.z = xadd(o.x, lb_step(T, m, n, o.L, o.g));
+            else o.z = xadd(o.x, lb_step<TL, NC>(T, m, n, o.L, o.g));
             o.d = mine ? xsub(o.z, o.x) : 0.0;
             // ---- lnsrlb: set up the search -----------------------------------------------------------------------
             T.sync();
@@ -578,7 +593,7 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             OT(1);
             o.stp = (o.nit == 0) ? fmin(xdiv(1.0, dnorm), LS_STPMAX) : 1.0;
             o.t = o.x; o.r = o.g; o.fold = o.f;
-            o.gd = opt_gd(T, m, n, o.g, o.d);
+            o.gd = opt_gd<TL, NC>(T, m, n, o.g, o.d);
             o.gdold = o.gd;
             o.ifun = 0;
             if (o.gd >= 0.0) o.ifun = maxls + 1;                                // not a descent direction: fail

@@ -26,15 +26,12 @@ using namespace neo;
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
 #ifndef NEO_TILE_MIN_PROBLEMS
-#define NEO_TILE_MIN_PROBLEMS 32768  // batch size from which short trajectories (M <= 4) run several problems per warp
+#define NEO_TILE_MIN_PROBLEMS 16384  // batch size from which short trajectories (M <= 4) run several problems per warp
                                      // (measured on B200: 16 k problems 11.1 vs 11.2 ms, 65 k 38.8 vs 43.2 ms)
 #endif
 #ifndef NEO_HOST_THREADS
 #define NEO_HOST_THREADS 8            // neo_optimize: host threads that assemble inputs / scatter results of a large batch
 #endif
-#ifndef NEO_PACKED_MIN_PER_SM
-#define NEO_PACKED_MIN_PER_SM 324    // problems x pieces per SM from which the 3-CTAs-per-SM instantiation is launched
-#endif                               // (measured break-even for one problem per warp: M = 10 near 4 k problems)
 
 struct OptArgs {
     int B, M, max_attempts;
@@ -84,7 +81,8 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // TL = 8 / 16: 4 / 2 problems per warp for short trajectories (n <= TL, 2M <= TL) -- with n = 7 decision variables and
 //   ~20 samples per piece a whole warp is mostly idle lanes; tiles cut the issue slots per evaluation ~2x.
 // MC: the number of pieces as a compile-time constant (loops over pieces/nodes unroll, lane maps fold).
-// MINB: CTAs per SM the register allocation is sized for.
+// MINB: CTAs per SM the register allocation is sized for (2: a third CTA would need 168 registers per thread and spill;
+// measured equal at best: 38.5 vs 38.6 ms on the dense-map workload).
 template <int MODE, int MC, int TL, int MINB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const DevParams P, const OptArgs a)
 {
@@ -164,7 +162,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
                 }
             }
             if (running) {
-                opt_advance(T, m, n, o, a.p_state + b, lower_ok);
+                opt_advance<TL, (MC > 0 ? 3 * MC - 2 : 0)>(T, m, n, o, a.p_state + b, lower_ok);
                 if (o.status != ST_RUNNING) { running = false; ended = true; report = true; }
             }
         }
@@ -834,10 +832,8 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
     void (*kern)(const DevParams, const OptArgs) = nullptr;
     const int TL = tile_lanes(h, a.B, a.M);
-    const bool packed = (size_t)a.B * a.M >= (size_t)NEO_PACKED_MIN_PER_SM * h->sm_count;    // M >= 5: 3 CTAs per SM
-    (void)packed;
     const bool staged = TL < 32;        // shared tiles: one staging block per tile (shared memory is what limits occupancy)
-#define NEO_KW(MODE, MC) (packed ? k_optimize<MODE, MC, 32, 3> : k_optimize<MODE, MC, 32, 2>)
+#define NEO_KW(MODE, MC) k_optimize<MODE, MC, 32, 2>
     switch (a.M) {
 #ifndef NEO_FAST_BUILD      // development builds (-DNEO_FAST_BUILD) instantiate M = 3 only
         case 2: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 8, 2> : k_optimize<SAMPLE_BY_PIECE, 2, 32, 2>; break;
