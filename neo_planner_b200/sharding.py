@@ -32,11 +32,17 @@ def record_width(M: int) -> int:
 def pack_records(res, M: int) -> np.ndarray:
     """dict of result arrays (neo_result) -> (B, record_width) float64 (integers are exact in fp64)."""
     B = res['x'].shape[0]
-    parts = [res['x'].reshape(B, -1), res['ts'].reshape(B, -1), res['coeffs'].reshape(B, -1), res['costs'].reshape(B, -1)]
-    parts += [res[k].reshape(B, 1).astype(np.float64) for k in INT_FIELDS]
-    rec = np.concatenate(parts, axis=1)
-    assert rec.shape[1] == record_width(M)
-    return np.ascontiguousarray(rec)
+    rec = np.empty((B, record_width(M)))
+    o = 0
+    for key in ('x', 'ts', 'coeffs', 'costs'):
+        a = res[key].reshape(B, -1)
+        rec[:, o:o + a.shape[1]] = a
+        o += a.shape[1]
+    for key in INT_FIELDS:
+        rec[:, o] = res[key]
+        o += 1
+    assert o == record_width(M)
+    return rec
 
 
 def unpack_records(rec: np.ndarray, M: int):
@@ -50,10 +56,24 @@ def unpack_records(rec: np.ndarray, M: int):
     return out
 
 
+_pinned = {}
+
+
+def _staging(name, shape, torch, pin):
+    """Reusable host staging tensors (pinned when a CUDA device is used) so that the copies can run asynchronously."""
+    key = (name, tuple(shape), pin)
+    t = _pinned.get(key)
+    if t is None:
+        t = torch.empty(shape, dtype=torch.float64, pin_memory=pin)
+        _pinned[key] = t
+    return t
+
+
 def gather_records(local_rec: np.ndarray, local_idx: np.ndarray, total: int, device=None, counts=None, offset: int = 0):
     """All-gather the per-rank records into global problem order on every rank. Ranks may own different counts:
     records are padded to the maximum count (one collective of fixed size, then the padding is dropped).
-    counts: per-rank record counts if the caller knows them (saves the object gather); offset is added to local_idx."""
+    counts: per-rank record counts if the caller knows them (saves the object gather); offset is added to local_idx.
+    On a CUDA device the records travel through pinned staging buffers (H2D, NCCL all-gather, D2H)."""
     import torch
     import torch.distributed as dist
     ws = dist.get_world_size()
@@ -62,18 +82,38 @@ def gather_records(local_rec: np.ndarray, local_idx: np.ndarray, total: int, dev
         counts = [None] * ws
         dist.all_gather_object(counts, int(local_rec.shape[0]))
     cap = max(counts)
-    dev = torch.device('cpu') if device is None else device
-    buf = torch.zeros((cap, width + 1), dtype=torch.float64, device=dev)
-    if local_rec.shape[0]:
-        buf[:local_rec.shape[0], :width] = torch.from_numpy(local_rec).to(dev)
-        buf[:local_rec.shape[0], width] = torch.from_numpy(np.asarray(local_idx, dtype=np.float64) + float(offset)).to(dev)
-    allbuf = torch.zeros((ws * cap, width + 1), dtype=torch.float64, device=dev)
+    dev = torch.device('cpu') if device is None else torch.device(device)
+    pin = dev.type == 'cuda'
+    nloc = local_rec.shape[0]
+    send = _staging('send', (cap, width + 1), torch, pin)
+    if nloc:
+        sv = send.numpy()
+        sv[:nloc, :width] = local_rec
+        sv[:nloc, width] = np.asarray(local_idx, dtype=np.float64) + float(offset)
+    buf = send.to(dev, non_blocking=True) if pin else send.clone()
+    allbuf = torch.empty((ws * cap, width + 1), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(allbuf, buf)
-    allbuf = allbuf.cpu().numpy().reshape(ws, cap, width + 1)
+    recv = _staging('recv', (ws * cap, width + 1), torch, pin)
+    recv.copy_(allbuf, non_blocking=pin)
+    if pin:
+        torch.cuda.current_stream(dev).synchronize()
+    rows_all = recv.numpy().reshape(ws, cap, width + 1)
+    starts = np.concatenate(([0], np.cumsum(counts)))
+    if all(c == 0 or (rows_all[r, 0, width] == starts[r] and rows_all[r, c - 1, width] == starts[r] + c - 1) for r, c in enumerate(counts)) \
+            and starts[-1] == total:
+        # ranks own contiguous blocks in rank order (the world-wise partition): no scatter, one copy per rank
+        out = np.empty((total, width))
+        for r, c in enumerate(counts):
+            idx = rows_all[r, :c, width]
+            if c and not np.array_equal(idx, np.arange(starts[r], starts[r] + c)):
+                break
+            out[starts[r]:starts[r] + c] = rows_all[r, :c, :width]
+        else:
+            return out
     out = np.zeros((total, width))
     seen = np.zeros(total, dtype=bool)
     for r in range(ws):
-        rows = allbuf[r, :counts[r]]
+        rows = rows_all[r, :counts[r]]
         idx = rows[:, width].astype(np.int64)
         out[idx] = rows[:, :width]
         seen[idx] = True

@@ -117,6 +117,13 @@ def test_config4_65536_problems_256_worlds():
     check_invariants(cfg, M, head, tail, out)
     # every one of the 65,536 problems against the CPU checker
     compare_with_checker(cfg, M, worlds, ids, head, tail, q0, ts0, rq, rts, out, np.arange(B), 0.985)
+    # trajectory sampling for all 65,536 problems in one call (the batch index used to sit on gridDim.y <= 65,535)
+    okm = out['ok'] == 1
+    states, count = h.sample(M, out['coeffs'], np.where(okm[:, None], out['ts'], 1.0), 10.0)
+    assert states.shape[0] == B and (count[okm] == np.ceil(out['ts'][okm].sum(1) * 10.0 - 1e-12).astype(int)).all()
+    assert np.abs(states[okm, 0, 0] - head[okm][:, 0]).max() < 1e-9                  # first sample = start position
+    last = B - 1 - int(np.argmax(okm[::-1]))
+    assert np.abs(states[last, 0, 0] - head[last, 0]).max() < 1e-9 and count[last] > 10
     # determinism: warps pick tasks in a different order every launch; results must not depend on it
     again = h.optimize(M, q0, ts0, head, tail, ids, rq, rts, 5)
     for k in ('x', 'ts', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):

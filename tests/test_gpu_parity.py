@@ -391,3 +391,21 @@ def test_batched_map_build_equals_single_builds():
         m = c_oracle.OracleMap.from_world(w)
         assert np.array_equal(b[0], m.esdf) and np.array_equal(b[1], m.gx) and np.array_equal(b[2], m.gy)
     print(f'{K} maps: {1e3 * (t1 - t0):.2f} ms one by one, {1e3 * (t2 - t1):.2f} ms in one call')
+
+
+def test_invalid_map_ids_are_rejected(world0):
+    """a map id that names no uploaded map must be an API error, not an out-of-bounds read or a silently
+    obstacle-free plan."""
+    cfg = YamlConfig()
+    head, tail = make_problems(world0, 4)
+    q0, ts0 = straight_line_guess(cfg, head, tail, 3)
+    h = lib.Handle(cfg, 0, 4)
+    h.set_map_occupancy(1, world0.H, world0.W, world0.res, world0.ox, world0.oy, world0.occ)
+    for ids in (np.array([1, 1, 7, 1], np.int32), np.array([1, -1, 1, 1], np.int32), np.array([1, 2, 1, 1], np.int32), None):
+        with pytest.raises(lib.NeoError, match='map'):
+            h.optimize(3, q0, ts0, head, tail, ids, max_attempts=1)
+        tau, _ = h.T2tau(ts0)
+        with pytest.raises(lib.NeoError, match='map'):
+            h.eval(3, np.concatenate([q0.reshape(4, -1), tau], axis=1), head, tail, ids)
+    out = h.optimize(3, q0, ts0, head, tail, np.array([1, 1, 1, 1], np.int32), max_attempts=1)      # the valid slot works
+    assert out['status'].max() <= 6
