@@ -845,7 +845,11 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
         case 9: kern = NEO_KW(SAMPLE_ALL_PIECES, 9); break;
         case 10: kern = NEO_KW(SAMPLE_ALL_PIECES, 10); break;
 #endif
+#ifdef NEO_EXP_RUNTIME_M
+        case 3: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 0, 8, 2> : k_optimize<SAMPLE_BY_PIECE, 0, 32, 2>; break;
+#else
         case 3: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 8, 2> : k_optimize<SAMPLE_BY_PIECE, 3, 32, 2>; break;
+#endif
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
 #undef NEO_KW
