@@ -381,6 +381,7 @@ struct neo_handle {
     MapView *d_maps = nullptr;
     unsigned int *d_counter = nullptr;
     std::vector<DevBuf> bufs;        // reusable device staging buffers for the host-pointer entry points
+    std::vector<cudaEvent_t> part_done;    // neo_optimize: a part of the results has arrived in pinned memory
     DevBuf pinned;                   // reusable pinned host staging buffer (neo_optimize)
     DevBuf astar;                    // per-warp search scratch of neo_astar (node records all-zero between launches)
     size_t astar_cap = 0;            // cells per warp the scratch is laid out for
@@ -505,6 +506,7 @@ extern "C" int neo_destroy(neo_handle *h)
     if (h->astar.p) cudaFree(h->astar.p);
     cudaFree(h->d_maps); cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    for (auto e : h->part_done) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
     return NEO_OK;
@@ -1093,8 +1095,8 @@ static void parallel_ranges(size_t count, F fn)
 }
 
 // Host-buffer entry: inputs are assembled in ONE pinned staging buffer that mirrors the device layout
-// (x0 = [q0, map_T2tau(ts0)], EP:207-211), moved with ONE H2D copy; results come back with ONE D2H copy and are
-// scattered into the caller's arrays. For large batches both host passes run on several threads (at 65,536 problems
+// (x0 = [q0, map_T2tau(ts0)], EP:207-211) in three stages, each copied while the next is assembled; results come back
+// in five parts, each scattered into the caller's arrays while the next is in flight. For large batches both host passes run on several threads (at 65,536 problems
 // they move 50 MB and take 196,608 logarithms -- a quarter of the kernel's time on one thread).
 static int optimize_host(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
                          const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
@@ -1134,6 +1136,8 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     int32_t *hst = (int32_t *)(hbase + L.st0);
     const neo_config cfg = h->cfg;
     std::atomic<int> any_bad_flag{0};
+    // three stages, each copied to the device while the next one is assembled
+    cudaStream_t st = h->stream;
     parallel_ranges(b, [&](size_t i0, size_t i1) {
         bool bad = false;
         for (size_t i = i0; i < i1; i++) {
@@ -1148,19 +1152,25 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
             hst[i] = s0;
             bad = bad || s0;
         }
+        if (bad) any_bad_flag.store(1);
+    });
+    CK(cudaMemcpyAsync(dbase + L.x0, hbase + L.x0, L.head - L.x0, cudaMemcpyHostToDevice, st));
+    const bool any_bad = any_bad_flag.load() != 0;
+    parallel_ranges(b, [&](size_t i0, size_t i1) {
         memcpy(hbase + L.head + 48 * i0, head + i0 * 6, 48 * (i1 - i0));
         memcpy(hbase + L.tail + 48 * i0, tail + i0 * 6, 48 * (i1 - i0));
         if (map_ids) memcpy(hbase + L.ids + 4 * i0, map_ids + i0, 4 * (i1 - i0));
-        if (A1) memcpy(hbase + L.rq + 8 * i0 * A1 * nq, retry_q + i0 * A1 * nq, 8 * (i1 - i0) * A1 * nq);
-        if (bad) any_bad_flag.store(1);
     });
-    const bool any_bad = any_bad_flag.load() != 0;
+    CK(cudaMemcpyAsync(dbase + L.head, hbase + L.head, L.rq - L.head, cudaMemcpyHostToDevice, st));     // head, tail, st0, ids
     double *rtau = (double *)(hbase + L.rtau);
     int rstatus = 0;
-    if (A1) for (int k = 0; k < M; k++) { rtau[k] = 0.0; const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
-
-    cudaStream_t st = h->stream;
-    CK(cudaMemcpyAsync(dbase, hbase, L.in_end, cudaMemcpyHostToDevice, st));
+    if (A1) {
+        for (int k = 0; k < M; k++) { rtau[k] = 0.0; const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
+        parallel_ranges(b, [&](size_t i0, size_t i1) {
+            memcpy(hbase + L.rq + 8 * i0 * A1 * nq, retry_q + i0 * A1 * nq, 8 * (i1 - i0) * A1 * nq);
+        });
+        CK(cudaMemcpyAsync(dbase + L.rq, hbase + L.rq, L.in_end - L.rq, cudaMemcpyHostToDevice, st));
+    }
     neo_result d;
     d.x = (double *)(dbase + L.x); d.ts = (double *)(dbase + L.ts); d.coeffs = (double *)(dbase + L.coeffs);
     d.costs = (double *)(dbase + L.costs);
@@ -1199,14 +1209,41 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
         CK(cudaMemcpyAsync(trace->status, td.status, 4 * tr_tasks * cap, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(trace->len, td.len, 4 * tr_tasks, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaMemcpyAsync(hbase + L.x, dbase + L.x, L.end - L.x, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // results: five device-to-host copies (x + ts, three thirds of the coefficients, the small fields); each part is
+    // scattered into the caller's arrays while the next one is in flight
+    while (h->part_done.size() < 5) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->part_done.push_back(e);
+    }
+    const size_t third = (b + 2) / 3;
+    const size_t c_lo[3] = {0, third < b ? third : b, 2 * third < b ? 2 * third : b}, c_hi[3] = {c_lo[1], c_lo[2], b};
+    CK(cudaMemcpyAsync(hbase + L.x, dbase + L.x, L.coeffs - L.x, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->part_done[0], st));
+    for (int k = 0; k < 3; k++) {
+        if (c_hi[k] > c_lo[k])
+            CK(cudaMemcpyAsync(hbase + L.coeffs + 8 * N2 * c_lo[k], dbase + L.coeffs + 8 * N2 * c_lo[k], 8 * N2 * (c_hi[k] - c_lo[k]),
+                               cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(h->part_done[1 + k], st));
+    }
+    CK(cudaMemcpyAsync(hbase + L.costs, dbase + L.costs, L.end - L.costs, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->part_done[4], st));
+    CK(cudaEventSynchronize(h->part_done[0]));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     parallel_ranges(b, [&](size_t i0, size_t i1) {
+        memcpy(out->x + i0 * n, hbase + L.x + 8 * i0 * n, 8 * (i1 - i0) * n);
+        memcpy(out->ts + i0 * M, hbase + L.ts + 8 * i0 * M, 8 * (i1 - i0) * M);
+    });
+    for (int k = 0; k < 3; k++) {
+        CK(cudaEventSynchronize(h->part_done[1 + k]));
+        const size_t lo = c_lo[k];
+        parallel_ranges(c_hi[k] - lo, [&](size_t i0, size_t i1) {
+            memcpy(out->coeffs + (lo + i0) * N2, hbase + L.coeffs + 8 * (lo + i0) * N2, 8 * (i1 - i0) * N2);
+        });
+    }
+    CK(cudaStreamSynchronize(st));
+    parallel_ranges(b, [&](size_t i0, size_t i1) {
         const size_t c = i1 - i0;
-        memcpy(out->x + i0 * n, hbase + L.x + 8 * i0 * n, 8 * c * n);
-        memcpy(out->ts + i0 * M, hbase + L.ts + 8 * i0 * M, 8 * c * M);
-        memcpy(out->coeffs + i0 * N2, hbase + L.coeffs + 8 * i0 * N2, 8 * c * N2);
         memcpy(out->costs + i0 * 4, hbase + L.costs + 32 * i0, 32 * c);
         memcpy(out->status + i0, hbase + L.status + 4 * i0, 4 * c);
         memcpy(out->ok + i0, hbase + L.ok + 4 * i0, 4 * c);
