@@ -485,28 +485,45 @@ __device__ __forceinline__ double lb_step(const Tile<TL> &T, const TileMem &m, i
     return d;
 }
 
+// the line-search state lives in shared memory between evaluations (28 registers that would otherwise stay live
+// across the evaluator); every lane of the tile holds the same values, the first lane writes them back
+template <int TL>
+__device__ __forceinline__ void ls_load(const Tile<TL> &T, const double *p, Dcsrch &S)
+{
+    S.finit = p[0]; S.ginit = p[1]; S.gtest = p[2]; S.width = p[3]; S.width1 = p[4]; S.stx = p[5]; S.fx = p[6]; S.gx = p[7];
+    S.sty = p[8]; S.fy = p[9]; S.gy = p[10]; S.stmin = p[11]; S.stmax = p[12];
+    const int flags = (int)p[13];
+    S.brackt = (flags & 1) != 0; S.stage = flags >> 1;
+}
+template <int TL>
+__device__ __forceinline__ void ls_store(const Tile<TL> &T, double *p, const Dcsrch &S)
+{
+    T.sync();
+    if (T.tl == 0) {
+        p[0] = S.finit; p[1] = S.ginit; p[2] = S.gtest; p[3] = S.width; p[4] = S.width1; p[5] = S.stx; p[6] = S.fx; p[7] = S.gx;
+        p[8] = S.sty; p[9] = S.fy; p[10] = S.gy; p[11] = S.stmin; p[12] = S.stmax;
+        p[13] = (double)((S.brackt ? 1 : 0) | (S.stage << 1));
+    }
+    T.sync();
+}
+
 // ---- the optimizer as a state machine around ONE evaluation site ------------------------------------------------------
 constexpr int ST_CANCELLED = 7;      // a speculative retry stopped because an earlier attempt was accepted (never reported)
 constexpr int ST_RUNNING = -1;
 
 struct OptState {
     double x, g, d, t, r, z, xlast;          // lane-owned components
-    double f, fold, stp, gd, gdold;
-    Dcsrch ls;
+    double f, stp, gd;                       // fold and gd_old of the running search: TileMem::ls[14], ls[15]
     LbMem L;
-    double costs[4];                         // at the last evaluated point (EP:233)
-    unsigned long long ns, nv, nc;
-    int nit, nfev, ifun, status;
+    int nit, nfev, ifun, status;             // (line-search state, last costs and work counters live in TileMem::ls / oc)
     bool first;
 };
 
 __device__ __forceinline__ void opt_begin(OptState &o, double x0l)
 {
     o.x = x0l; o.g = 0.0; o.d = 0.0; o.t = 0.0; o.r = 0.0; o.z = 0.0; o.xlast = 0.0;
-    o.f = 0.0; o.fold = 0.0; o.stp = 0.0; o.gd = 0.0; o.gdold = 0.0;
+    o.f = 0.0; o.stp = 0.0; o.gd = 0.0;
     o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0;
-    o.costs[0] = o.costs[1] = o.costs[2] = o.costs[3] = 0.0;
-    o.ns = o.nv = o.nc = 0;
     o.nit = 0; o.nfev = 0; o.ifun = 0; o.status = ST_RUNNING; o.first = true;
 }
 
@@ -547,7 +564,10 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
         new_dir = true;
     } else {
         o.gd = opt_gd<TL, NC>(T, m, n, o.g, o.d);
-        const int ls_task = dcsrch_step(o.ls, o.stp, o.f, o.gd);
+        Dcsrch ls;
+        ls_load(T, m.ls, ls);
+        const int ls_task = dcsrch_step(ls, o.stp, o.f, o.gd);
+        if (ls_task == 0) ls_store(T, m.ls, ls);
         OT(0);
         if (ls_task == 0) new_dir = false;                                       // FG: another trial point
         else {
@@ -559,7 +579,8 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
                 if (T.shfl(w, 0) & cancel_mask) { o.status = ST_CANCELLED; return; }
             }
             if (T.dmax(mine ? fabs(o.g) : 0.0) <= pgtol) { o.status = 1; return; }
-            if (xsub(o.fold, o.f) <= xmul(tol, max3(fabs(o.fold), fabs(o.f), 1.0))) { o.status = 0; return; }
+            const double fold = m.ls[14], gdold = m.ls[15];
+            if (xsub(fold, o.f) <= xmul(tol, max3(fabs(fold), fabs(o.f), 1.0))) { o.status = 0; return; }
             if (o.nit >= maxiter || o.nfev > maxfun) { o.status = 3; return; }
             const double y = xsub(o.g, o.r);                                       // matupd
             T.sync();
@@ -570,8 +591,8 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             const double rr = xmul(nr, nr);
             OT(1);
             double dr, ddum, s;
-            if (o.stp == 1.0) { dr = xsub(o.gd, o.gdold); ddum = -o.gdold; s = o.d; }
-            else { dr = xmul(xsub(o.gd, o.gdold), o.stp); s = xmul(o.d, o.stp); ddum = xmul(-o.gdold, o.stp); }
+            if (o.stp == 1.0) { dr = xsub(o.gd, gdold); ddum = -gdold; s = o.d; }
+            else { dr = xmul(xsub(o.gd, gdold), o.stp); s = xmul(o.d, o.stp); ddum = xmul(-gdold, o.stp); }
             if (!(dr <= xmul(epsmch, ddum))) lb_update<TL, NC>(T, m, n, o.L, s, y, rr, dr);
             new_dir = true;
         }
@@ -592,18 +613,20 @@ __device__ __forceinline__ void opt_advance(const Tile<TL> &T, const TileMem &m,
             const double dnorm = nrm2_x87(n, m.dv);
             OT(1);
             o.stp = (o.nit == 0) ? fmin(xdiv(1.0, dnorm), LS_STPMAX) : 1.0;
-            o.t = o.x; o.r = o.g; o.fold = o.f;
+            o.t = o.x; o.r = o.g;
             o.gd = opt_gd<TL, NC>(T, m, n, o.g, o.d);
-            o.gdold = o.gd;
+            T.sync();
+            if (T.tl == 0) { m.ls[14] = o.f; m.ls[15] = o.gd; }
             o.ifun = 0;
             if (o.gd >= 0.0) o.ifun = maxls + 1;                                // not a descent direction: fail
-            else dcsrch_start(o.ls, o.stp, o.f, o.gd);
+            else { Dcsrch ls; dcsrch_start(ls, o.stp, o.f, o.gd); ls_store(T, m.ls, ls); }
             OT(14);
         }
         o.ifun++;
         if (o.ifun - 1 < maxls) break;                                          // evaluate the trial point
         // ---- failed search: restore the iterate; ABNORMAL if the memory is already empty --------------------------
-        o.x = o.t; o.g = o.r; o.f = o.fold;
+        T.sync();
+        o.x = o.t; o.g = o.r; o.f = m.ls[14];
         if (o.L.col == 0) { o.status = 2; return; }
         o.L.col = 0; o.L.head = 0; o.L.iupdat = 0; o.L.theta = 1.0;
         new_dir = true;

@@ -116,6 +116,8 @@ struct TileMem {
     double *dr;    // [HIST]   diagonal of S'Y as matupd stores it ((gd - gdold) * stp), by ring slot
     double *gv;    // [n]      g and d as vectors every lane can read (sequential inner products)
     double *dv;    // [n]
+    double *ls;    // [16]     line-search state (Dcsrch) between evaluations, f and g'd at the start of the search
+    double *oc;    // [7]      costs at the last evaluated point (4), work counters samples / violating / colliding (3)
     // one region, two users: per-lane partial sums of the sample loop (evaluation) / the factored middle matrix (direction)
     double *red;   // [15 or 15*M][TL+1] per-lane partial sums of the sample loop (padded rows)
     double *wn;    // [LBW(LBW+1)/2] packed upper triangle, column j at j(j+1)/2; then wv [LBW]
@@ -126,7 +128,10 @@ struct TileMem {
 
 // staging rows of the sample loop's partial sums: one block of 15 rows per piece when all pieces are parked before the
 // owners add them (by-piece schedule, latency-optimised), one block otherwise (see eval_fg)
-__host__ __device__ inline int red_doubles(int M, int TL, bool one_block) { return (M > 4 || one_block) ? 15 * (TL + 1) : 15 * (TL + 1) * M; }
+// rows are padded to TL + 1 for a full warp (conflict-free owner reads); narrow tiles are not padded (their shared memory
+// decides how many problems an SM holds)
+__host__ __device__ constexpr int red_stride(int TL) { return TL == 32 ? 33 : TL; }
+__host__ __device__ inline int red_doubles(int M, int TL, bool one_block) { return (M > 4 || one_block) ? 15 * red_stride(TL) : 15 * red_stride(TL) * M; }
 
 // Layout of a tile's slice. Shared memory is what limits the number of problems in flight per SM, so regions whose
 // lifetimes do not overlap share storage:
@@ -157,7 +162,7 @@ __host__ __device__ inline int scratch_doubles(int M, int TL, bool one_block)
 __host__ __device__ inline int tile_mem_doubles(int M, int TL = 32, bool one_block = false)
 {
     const int n = 3 * M - 2;
-    int tot = 12 + scratch_doubles(M, TL, one_block) + 2 * HIST * n + HIST * HIST + 2 * HIST + 2 * n + (M > 4 ? 2 * M + M + 32 : 0);
+    int tot = 12 + scratch_doubles(M, TL, one_block) + 2 * HIST * n + HIST * HIST + 2 * HIST + 2 * n + 16 + 7 + (M > 4 ? 2 * M + M + 32 : 0);
     return (tot + 1) & ~1;
 }
 
@@ -194,6 +199,8 @@ __device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block
     m.dr = base; base += HIST;
     m.gv = base; base += n;
     m.dv = base; base += n;
+    m.ls = base; base += 16;
+    m.oc = base; base += 7;
     m.lw = base; m.nsprev = base + 2 * M; m.asg = base + 3 * M;      // only carved for M > 4 (see tile_mem_doubles)
     return m;
 }
@@ -510,13 +517,13 @@ __device__ __forceinline__ void eval_fg(const Tile<TL> &T, const DevParams &P, c
 #pragma unroll
             for (int s2 = 0; s2 < 16; s2++) acc[s2] = 0.0;
             for (int j = lane; j < ns; j += TL) sample_point(P, map, cx, cy, j, ns, inv_ns, want_grad, acc, out, bad);
-            double *row = m.red + (STAGED ? 0 : 15 * i) * (TL + 1) + lane;
+            double *row = m.red + (STAGED ? 0 : 15 * i) * red_stride(TL) + lane;
 #pragma unroll
-            for (int s2 = 0; s2 < 15; s2++) row[s2 * (TL + 1)] = acc[s2];
+            for (int s2 = 0; s2 < 15; s2++) row[s2 * red_stride(TL)] = acc[s2];
             if (STAGED) {
                 T.sync();
                 for (int o = lane; o < 15; o += TL) {
-                    const double *p = m.red + o * (TL + 1);
+                    const double *p = m.red + o * red_stride(TL);
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                     for (int k = 0; k < TL; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
@@ -531,7 +538,7 @@ __device__ __forceinline__ void eval_fg(const Tile<TL> &T, const DevParams &P, c
         if (!STAGED) {
             T.sync();
             for (int o = lane; o < 15 * M; o += TL) {
-                const double *p = m.red + o * (TL + 1);
+                const double *p = m.red + o * red_stride(TL);
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                 for (int k = 0; k < TL; k += 4) { a0 += p[k]; a1 += p[k + 1]; a2 += p[k + 2]; a3 += p[k + 3]; }
