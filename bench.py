@@ -324,13 +324,12 @@ def e2e_run(torch, dist, run, wl, lib, Ke, distributed, world_size, dev):
     h, M, B = run.h, wl['M'], wl['B']
     out_host = lib.Handle.alloc_result(B, M)
     hp, tp = lib.pad_state(wl['head']), lib.pad_state(wl['tail'])
-    idx = np.arange(B)
 
     def step():
         h.optimize(M, wl['q0'], wl['ts0'], hp, tp, wl['map_ids'], wl['retry_q'], wl['retry_ts'], 5, out=out_host)
         if distributed:
             rec = sharding.pack_records(out_host, M)
-            sharding.gather_records(rec, idx, B * world_size, dev, counts=[B] * world_size, offset=dist.get_rank() * B)
+            sharding.gather_blocks(rec, [B] * world_size, dev)          # every rank ends with all records, in global order
     for _ in range(2):
         step()
     torch.cuda.synchronize()

@@ -24,10 +24,12 @@
  *   same stream, and maps must not be re-uploaded while a launch is in flight. Use one handle per concurrent stream.
  *   map_ids passed to host-pointer entry points are validated (every id must name a slot that holds a map, else
  *   NEO_ERR_INVALID); for _dev entry points that is a precondition (the ids are in device memory).
- *   Kernel selection: problems with M <= 4 pieces run one per warp below NEO_TILE_MIN_PROBLEMS (16384) problems per call
- *   and 4 (M <= 3) or 2 (M = 4) per warp from there on; results of the two schedules differ in the last bits of the
- *   sampled sums (different partial-sum order), never in the algorithm. The one development switch read from the
- *   environment at neo_create, NEO_TILE = 8 | 16 | 32, pins the lanes per problem (A/B measurements, parity tests).
+ *   Kernel selection: problems with M <= 4 pieces run one per warp below NEO_TILE_MIN_PROBLEMS (8192) problems per call
+ *   and 4 (M <= 3) or 2 (M = 4) per warp from there on (one CTA per SM whose warps start their evaluations in groups);
+ *   results of the two schedules differ in the last bits of the sampled sums (different partial-sum order), never in
+ *   the algorithm. Development switches read from the environment at neo_create (A/B measurements, parity tests):
+ *   NEO_TILE = 8 | 16 | 32 pins the lanes per problem, NEO_GROUPED = 0 turns the grouped starts off, NEO_GROUP_WARPS
+ *   sets the group size.
  */
 #ifndef NEOOPT_H
 #define NEOOPT_H

@@ -26,7 +26,7 @@ using namespace neo;
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
 #ifndef NEO_TILE_MIN_PROBLEMS
-#define NEO_TILE_MIN_PROBLEMS 16384  // batch size from which short trajectories (M <= 4) run several problems per warp
+#define NEO_TILE_MIN_PROBLEMS 8192  // batch size from which short trajectories (M <= 4) run several problems per warp
                                      // (measured on B200: 16 k problems 11.1 vs 11.2 ms, 65 k 38.8 vs 43.2 ms)
 #endif
 #ifndef NEO_HOST_THREADS
@@ -55,6 +55,7 @@ struct OptArgs {
     long long *work;
     // optional evaluation trace (neo_optimize_trace; all null otherwise): per task the first trace_cap evaluations
     int trace_cap;
+    int bus_q;                               // SM-wide variant: warps per departing group at the evaluation site
     double *tr_x, *tr_f, *tr_g, *tr_costs;   // (A*B, cap, n), (A*B, cap), (A*B, cap, n), (A*B, cap, 4)
     int32_t *tr_status, *tr_len;             // (A*B, cap), (A*B)
 };
@@ -83,8 +84,11 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // MC: the number of pieces as a compile-time constant (loops over pieces/nodes unroll, lane maps fold).
 // MINB: CTAs per SM the register allocation is sized for (2: a third CTA would need 168 registers per thread and spill;
 // measured equal at best: 38.5 vs 38.6 ms on the dense-map workload).
-template <int MODE, int MC, int TL, int MINB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const DevParams P, const OptArgs a)
+#ifdef NEO_ROUND_TRACE
+__device__ long long g_round_trace[12 * 2048 * 4];      // development probe: per warp of CTA 0, per round: arrive, go, evaluated, advanced
+#endif
+template <int MODE, int MC, int TL, int MINB, int WPC = WARPS_PER_CTA>
+__global__ void __launch_bounds__(WPC * 32, MINB) k_optimize(const DevParams P, const OptArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,8 +107,54 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
     size_t b = 0;
     int map_id = 0;              // the MapView itself (14 registers) is re-read from device memory at every evaluation
     unsigned long long t_start = 0;
+    __shared__ unsigned s_arrivals;
+    constexpr unsigned BUS_DRAIN = 0x80000000u;
+    bool drained = false;
+    if constexpr (WPC > WARPS_PER_CTA) {
+        if (threadIdx.x == 0) s_arrivals = 0;
+        __syncthreads();
+    }
+#ifdef NEO_ROUND_TRACE
+    int rt_round = 0;
+#endif
     for (;;) {
-        if (__all_sync(FULL, retired)) break;
+#ifdef NEO_ROUND_TRACE
+        if (blockIdx.x == 0 && lane == 0 && rt_round < 2048) g_round_trace[(warp * 2048 + rt_round) * 4 + 0] = clock64();
+#endif
+        if constexpr (WPC > WARPS_PER_CTA) {
+            // departures in groups: a warp arriving at the evaluation site takes a ticket and waits on a hardware
+            // barrier until the bus_q warps of its group have gathered, so that the group walks the evaluator's code
+            // together and shares its instruction fetches. The first warp that runs out of tasks ends the scheme: later
+            // tickets carry the drain flag (no waiting any more) and it completes the one partially filled group.
+            __syncwarp();
+            if (!drained) {
+                unsigned k = 0;
+                if (lane == 0) k = atomicAdd(&s_arrivals, 1u);
+                k = __shfl_sync(FULL, k, 0);
+                if (k & BUS_DRAIN) drained = true;
+                else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((k / (unsigned)a.bus_q) & 7u)), "r"(a.bus_q * 32) : "memory");
+            }
+        }
+#ifdef NEO_ROUND_TRACE
+        if (blockIdx.x == 0 && lane == 0 && rt_round < 2048) g_round_trace[(warp * 2048 + rt_round) * 4 + 1] = clock64();
+        const int rt_now = rt_round++;
+#endif
+        if (__all_sync(FULL, retired)) {
+            if constexpr (WPC > WARPS_PER_CTA) {
+                if (!drained) {
+                    unsigned old = 0;
+                    if (lane == 0) old = atomicOr(&s_arrivals, BUS_DRAIN);
+                    old = __shfl_sync(FULL, old, 0);
+                    if (!(old & BUS_DRAIN)) {          // tickets issued so far: old; the last group holds old % bus_q warps
+                        const unsigned waiting = old % (unsigned)a.bus_q, g = old / (unsigned)a.bus_q;
+                        if (waiting)
+                            for (unsigned i = waiting; i < (unsigned)a.bus_q; i++)
+                                asm volatile("bar.arrive %0, %1;" ::"r"(1 + (int)(g & 7u)), "r"(a.bus_q * 32) : "memory");
+                    }
+                }
+            }
+            break;
+        }
         bool ended = false, report = false;      // this tile's task ended in this round / it has a record to write
         if (!running && !retired) {
             unsigned t0 = 0;
@@ -149,6 +199,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
                 OT_BEGIN;
                 eval_fg<MODE, TL>(T, P, a.maps[map_id], m, M, o.x, true, ev);
                 OT(16);
+#ifdef NEO_ROUND_TRACE
+                if (blockIdx.x == 0 && lane == 0 && rt_now < 2048) g_round_trace[(warp * 2048 + rt_now) * 4 + 2] = clock64();
+#endif
                 if (T.tl == 0) { m.oc[4] += (double)ev.ns; m.oc[5] += (double)ev.nv; m.oc[6] += (double)ev.nc; }   // exact below 2^53
                 if (a.tr_x && o.nfev < a.trace_cap) {
                     const size_t k = (size_t)tid * a.trace_cap + o.nfev;
@@ -167,6 +220,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) k_optimize(const Dev
                 if (o.status != ST_RUNNING) { running = false; ended = true; report = true; }
             }
         }
+#ifdef NEO_ROUND_TRACE
+        __syncwarp();
+        if (blockIdx.x == 0 && lane == 0 && rt_now < 2048) g_round_trace[(warp * 2048 + rt_now) * 4 + 3] = clock64();
+#endif
         if (!ended) continue;
 
         // ---- the task ended: record it, mark it in the problem's state word -------------------------------------
@@ -392,6 +449,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    int grouped = -1, group_warps = 0;   // development switches (env NEO_GROUPED = 0 | 1, NEO_GROUP_WARPS at neo_create; -1 / 0: by batch size)
     int tile = 0;                    // development switch (env NEO_TILE = 8 | 16 | 32 at neo_create; 0: by batch size):
                                      // lanes per problem for M <= 4, see launch_optimize / include/neoopt.h
     int sm_count = 0, cc_major = 0, cc_minor = 0;
@@ -479,6 +537,8 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     }
     neo_handle *h = new neo_handle();
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps); h->views.resize(max_maps);
+    if (const char *e = getenv("NEO_GROUPED")) h->grouped = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("NEO_GROUP_WARPS")) h->group_warps = atoi(e);
     if (const char *e = getenv("NEO_TILE")) { const int t = atoi(e); h->tile = (t == 8 || t == 16 || t == 32) ? t : 0; }
     h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
@@ -803,17 +863,17 @@ static int check_map_ids(neo_handle *h, int B, const int32_t *map_ids, const cha
     return NEO_OK;
 }
 
-static size_t smem_bytes(int M, int TL = 32, bool one_block = false)
+static size_t smem_bytes(int M, int TL = 32, bool one_block = false, int wpc = WARPS_PER_CTA)
 {
-    return sizeof(double) * (size_t)tile_mem_doubles(M, TL, one_block) * WARPS_PER_CTA * (32 / TL);
+    return sizeof(double) * (size_t)tile_mem_doubles(M, TL, one_block) * wpc * (32 / TL);
 }
 
 template <typename K>
-static int prep_kernel(neo_handle *h, K kernel, size_t smem, int *ctas_per_sm)
+static int prep_kernel(neo_handle *h, K kernel, size_t smem, int *ctas_per_sm, int wpc = WARPS_PER_CTA)
 {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, WARPS_PER_CTA * 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, wpc * 32, smem));
     if (occ < 1) return fail(h, "kernel does not fit on an SM");
     *ctas_per_sm = occ;
     return NEO_OK;
@@ -829,19 +889,34 @@ static int tile_lanes(const neo_handle *h, int B, int M)
     return B >= NEO_TILE_MIN_PROBLEMS ? small : 32;
 }
 
+typedef void (*OptKernel)(const DevParams, const OptArgs);
+template <int MODE, int MC, int TL, int MINB>
+static OptKernel pick_optimize(bool grouped, int *wpc)
+{
+    if (grouped) { *wpc = 4 * MINB; return k_optimize<MODE, MC, TL, 1, 4 * MINB>; }
+    return k_optimize<MODE, MC, TL, MINB, WARPS_PER_CTA>;
+}
+
 static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 {
     int occ;
     // kernel variant: lanes per problem (tile_lanes) and sampling schedule (minco_tile.cuh) by trajectory length; one
-    // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x)
+    // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x). The tile variants (several problems
+    // per warp, large batches) exist twice: CTAs of 4 warps, several per SM, and ONE CTA of all the SM's warps whose warps
+    // leave the evaluation site in groups of 2/3 of the CTA, sharing their instruction fetches: 27.1 vs 33.9 ms on config
+    // 4, 8.5 vs 10.5 ms at 16,384 problems. One problem per warp: no gain (38.6 -> 39.7 ms on config 5), plain only.
     void (*kern)(const DevParams, const OptArgs) = nullptr;
     const int TL = tile_lanes(h, a.B, a.M);
     const bool staged = TL < 32;        // shared tiles: one staging block per tile (shared memory is what limits occupancy)
+    bool grouped = TL < 32;
+    if (h->grouped >= 0) grouped = grouped && h->grouped != 0;
+    int wpc = WARPS_PER_CTA;
+#define NEO_PICK(MODE, MC, TLV, MINB) pick_optimize<MODE, MC, TLV, MINB>(grouped, &wpc)
 #define NEO_KW(MODE, MC) k_optimize<MODE, MC, 32, 2>
     switch (a.M) {
 #ifndef NEO_FAST_BUILD      // development builds (-DNEO_FAST_BUILD) instantiate M = 3 only
-        case 2: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 2, 8, 3> : k_optimize<SAMPLE_BY_PIECE, 2, 32, 2>; break;
-        case 4: kern = TL == 16 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 4, 16, 2> : k_optimize<SAMPLE_BY_PIECE, 4, 32, 2>; break;
+        case 2: kern = TL == 8 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 2, 8, 3) : NEO_KW(SAMPLE_BY_PIECE, 2); break;
+        case 4: kern = TL == 16 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 4, 16, 2) : NEO_KW(SAMPLE_BY_PIECE, 4); break;
         case 5: kern = NEO_KW(SAMPLE_ALL_PIECES, 5); break;
         case 6: kern = NEO_KW(SAMPLE_ALL_PIECES, 6); break;
         case 7: kern = NEO_KW(SAMPLE_ALL_PIECES, 7); break;
@@ -849,16 +924,19 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
         case 9: kern = NEO_KW(SAMPLE_ALL_PIECES, 9); break;
         case 10: kern = NEO_KW(SAMPLE_ALL_PIECES, 10); break;
 #endif
-        // 8-lane tiles: three CTAs (12 warps, 168 registers, no spills) per SM; measured 33.1 vs 34.8 ms on config 4
-        case 3: kern = TL == 8 ? k_optimize<SAMPLE_BY_PIECE_STAGED, 3, 8, 3> : k_optimize<SAMPLE_BY_PIECE, 3, 32, 2>; break;
+        // 8-lane tiles: 12 warps per SM (168 registers, no spills); measured 33.1 vs 34.8 ms for 8 warps on config 4
+        case 3: kern = TL == 8 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 3, 8, 3) : NEO_KW(SAMPLE_BY_PIECE, 3); break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
 #undef NEO_KW
-    const size_t smem = smem_bytes(a.M, TL, staged);
-    int rc = prep_kernel(h, kern, smem, &occ);
+#undef NEO_PICK
+    a.bus_q = h->group_warps > 0 ? h->group_warps : 3 * wpc / 4;        // 12 warps: 9 (26.4 ms; 8: 26.5, 10: 26.9, 6: 27.9, 12: 30.2)
+    if (a.bus_q > wpc) a.bus_q = wpc;
+    const size_t smem = smem_bytes(a.M, TL, staged, wpc);
+    int rc = prep_kernel(h, kern, smem, &occ, wpc);
     if (rc) return rc;
     const size_t tasks = (size_t)a.B * a.max_attempts, n = 3 * a.M - 2;
-    const size_t per_cta = (size_t)WARPS_PER_CTA * (32 / TL);
+    const size_t per_cta = (size_t)wpc * (32 / TL);
     const size_t need = (tasks + per_cta - 1) / per_cta;
     const int grid = (int)(need < (size_t)occ * h->sm_count ? need : (size_t)occ * h->sm_count);
     // per-task scratch records + per-problem state word (library-owned, grow-only)
@@ -873,7 +951,7 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     a.counter = h->d_counter;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     CK(cudaMemsetAsync(a.p_state, 0, sizeof(unsigned) * a.B, st));
-    kern<<<grid, WARPS_PER_CTA * 32, smem, st>>>(dev_params(h->cfg), a);
+    kern<<<grid, wpc * 32, smem, st>>>(dev_params(h->cfg), a);
     h->launches++;
     CK(cudaGetLastError());
     return NEO_OK;
@@ -1530,6 +1608,15 @@ extern "C" int neo_test_exp_dev(neo_handle *h, int n, const double *x, double *y
     CK(cudaStreamSynchronize(h->stream));
     return NEO_OK;
 }
+
+#ifdef NEO_ROUND_TRACE
+extern "C" int neo_test_round_trace(long long *out)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_round_trace, sizeof(long long) * 12 * 2048 * 4);
+    return NEO_OK;
+}
+#endif
 
 #ifdef NEO_OPT_TICKS
 // development probe: read and clear the optimizer's phase counters (cycles [0..32), calls [32..64))

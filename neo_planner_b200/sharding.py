@@ -69,6 +69,33 @@ def _staging(name, shape, torch, pin):
     return t
 
 
+def gather_blocks(local_rec: np.ndarray, counts, device=None):
+    """All-gather for the usual partition: rank r owns a CONTIGUOUS block of counts[r] problems and the blocks follow
+    each other in rank order (shard_problems on a world-sorted problem list). No index column, no scatter: the blocks
+    are padded to the largest count, gathered with ONE collective and land in global order. Returns (sum(counts),
+    width); with equal counts this is a view of the reusable (pinned) staging buffer -- valid until the next call."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size()
+    assert len(counts) == ws and local_rec.shape[0] == counts[dist.get_rank()]
+    width, cap = local_rec.shape[1], max(counts)
+    dev = torch.device('cpu') if device is None else torch.device(device)
+    pin = dev.type == 'cuda'
+    send = _staging('send_blocks', (cap, width), torch, pin)
+    send.numpy()[:local_rec.shape[0]] = local_rec
+    buf = send.to(dev, non_blocking=True) if pin else send
+    allbuf = torch.empty((ws * cap, width), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allbuf, buf)
+    recv = _staging('recv_blocks', (ws * cap, width), torch, pin)
+    recv.copy_(allbuf, non_blocking=pin)
+    if pin:
+        torch.cuda.current_stream(dev).synchronize()
+    rows = recv.numpy()
+    if all(c == cap for c in counts):
+        return rows
+    return np.concatenate([rows[r * cap:r * cap + c] for r, c in enumerate(counts)], axis=0)
+
+
 def gather_records(local_rec: np.ndarray, local_idx: np.ndarray, total: int, device=None, counts=None, offset: int = 0):
     """All-gather the per-rank records into global problem order on every rank. Ranks may own different counts:
     records are padded to the maximum count (one collective of fixed size, then the padding is dropped).
@@ -146,5 +173,12 @@ class ShardedPlanner:
         if self.world_size == 1:
             full = np.zeros((len(head), rec.shape[1])); full[idx] = rec
         else:
-            full = gather_records(rec, idx, len(head), self.device)
+            # every rank knows the whole problem list, hence every rank's share: contiguous blocks in rank order (a
+            # world-sorted list) take the scatter-free path
+            shares = [shard_problems(world_of_problem, self.world_size, r) for r in range(self.world_size)]
+            blocks = np.concatenate(shares)
+            if np.array_equal(blocks, np.arange(len(head))):
+                full = gather_blocks(rec, [len(s) for s in shares], self.device)
+            else:
+                full = gather_records(rec, idx, len(head), self.device, counts=[len(s) for s in shares])
         return unpack_records(full, self.M)

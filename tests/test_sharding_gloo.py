@@ -30,11 +30,19 @@ def problems(n_worlds=5, per_world=(3, 9, 1, 4, 6)):
     return rng.normal(size=(B, 2, 2)), rng.normal(size=(B, 2, 2)), wid
 
 
-def _worker(rank, world_size, port, q):
+def shuffled(head, tail, wid):
+    """The same problems in an order that interleaves the worlds: a rank's share is no longer one contiguous block."""
+    perm = np.random.default_rng(5).permutation(len(wid))
+    return head[perm], tail[perm], wid[perm]
+
+
+def _worker(rank, world_size, port, q, shuffle=False):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world_size)
     head, tail, wid = problems()
+    if shuffle:
+        head, tail, wid = shuffled(head, tail, wid)
     sp = sharding.ShardedPlanner(fake_solve, M, rank, world_size)
     res = sp.plan(head, tail, wid)
     q.put((rank, res))
@@ -64,13 +72,16 @@ def test_pack_unpack_roundtrip():
 
 
 @pytest.mark.timeout(120)
-def test_two_rank_gather_matches_single_process():
+@pytest.mark.parametrize('shuffle', [False, True], ids=['contiguous-blocks', 'interleaved'])
+def test_two_rank_gather_matches_single_process(shuffle):
     head, tail, wid = problems()
+    if shuffle:
+        head, tail, wid = shuffled(head, tail, wid)
     single = sharding.ShardedPlanner(fake_solve, M, 0, 1).plan(head, tail, wid)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, shuffle)) for r in range(2)]
     for p in procs:
         p.start()
     out = dict(q.get(timeout=100) for _ in range(2))
