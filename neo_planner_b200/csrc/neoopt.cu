@@ -25,6 +25,9 @@ using namespace neo;
 // kernels
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WARPS_PER_CTA = 4;
+#ifndef NEO_GROUPED_MIN_PROBLEMS
+#define NEO_GROUPED_MIN_PROBLEMS 2048 // batch size from which one-problem-per-warp kernels run as one CTA per SM with grouped starts
+#endif
 #ifndef NEO_TILE_MIN_PROBLEMS
 #define NEO_TILE_MIN_PROBLEMS 8192  // batch size from which short trajectories (M <= 4) run several problems per warp
                                      // (measured on B200: 16 k problems 11.1 vs 11.2 ms, 65 k 38.8 vs 43.2 ms)
@@ -82,8 +85,14 @@ __device__ __forceinline__ bool resolved(unsigned st, int A)
 // TL = 8 / 16: 4 / 2 problems per warp for short trajectories (n <= TL, 2M <= TL) -- with n = 7 decision variables and
 //   ~20 samples per piece a whole warp is mostly idle lanes; tiles cut the issue slots per evaluation ~2x.
 // MC: the number of pieces as a compile-time constant (loops over pieces/nodes unroll, lane maps fold).
-// MINB: CTAs per SM the register allocation is sized for (2: a third CTA would need 168 registers per thread and spill;
-// measured equal at best: 38.5 vs 38.6 ms on the dense-map workload).
+// MINB x WPC: CTAs per SM the register allocation is sized for x warps per CTA: 3 x 4 (plain) or 1 x 12 (grouped starts,
+// see launch_optimize). The optimizer's line-search record, costs and counters live in shared memory, so 168 registers
+// per thread hold the rest without spills.
+// Grouped starts: this loop is ~55 KB of code walked once per round by every warp, against a 32 KB instruction cache per
+// SM and a GPC-level instruction path that saturates (ncu: gcc__cache_requests_type_instruction 95 % of peak, 53 % of
+// the stall samples `no_instruction`). Warps that walk the code TOGETHER share every fetched line (devtools/
+// icache_share.cu: 12 warps in step run a 96 KB body at 3.6 IPC per SM, spread out at 2.5), but a barrier over all 12
+// warps waits for the slowest search direction every round (40 % barrier stalls). Groups of nine are the measured optimum.
 #ifdef NEO_ROUND_TRACE
 __device__ long long g_round_trace[12 * 2048 * 4];      // development probe: per warp of CTA 0, per round: arrive, go, evaluated, advanced
 #endif
@@ -901,18 +910,19 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
 {
     int occ;
     // kernel variant: lanes per problem (tile_lanes) and sampling schedule (minco_tile.cuh) by trajectory length; one
-    // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x). The tile variants (several problems
-    // per warp, large batches) exist twice: CTAs of 4 warps, several per SM, and ONE CTA of all the SM's warps whose warps
-    // leave the evaluation site in groups of 2/3 of the CTA, sharing their instruction fetches: 27.1 vs 33.9 ms on config
-    // 4, 8.5 vs 10.5 ms at 16,384 problems. One problem per warp: no gain (38.6 -> 39.7 ms on config 5), plain only.
+    // instantiation per supported piece count (loops over pieces/nodes unroll: 1.27x). Every variant is sized for 12 warps
+    // per SM (168 registers, no spills: config 5 38.7 -> 33.2 ms against 8 warps) and exists twice: three CTAs of 4 warps
+    // per SM (small batches: spread over all SMs, nobody waits) and ONE CTA of 12 warps whose warps leave the evaluation
+    // site in groups of nine, sharing their instruction fetches (config 4 33.9 -> 26.4 ms, config 5 33.2 -> 30.5 ms,
+    // neutral at 2,048 problems).
     void (*kern)(const DevParams, const OptArgs) = nullptr;
     const int TL = tile_lanes(h, a.B, a.M);
     const bool staged = TL < 32;        // shared tiles: one staging block per tile (shared memory is what limits occupancy)
-    bool grouped = TL < 32;
-    if (h->grouped >= 0) grouped = grouped && h->grouped != 0;
+    bool grouped = TL < 32 || a.B >= NEO_GROUPED_MIN_PROBLEMS;
+    if (h->grouped >= 0) grouped = h->grouped != 0;
     int wpc = WARPS_PER_CTA;
 #define NEO_PICK(MODE, MC, TLV, MINB) pick_optimize<MODE, MC, TLV, MINB>(grouped, &wpc)
-#define NEO_KW(MODE, MC) k_optimize<MODE, MC, 32, 2>
+#define NEO_KW(MODE, MC) NEO_PICK(MODE, MC, 32, 3)
     switch (a.M) {
 #ifndef NEO_FAST_BUILD      // development builds (-DNEO_FAST_BUILD) instantiate M = 3 only
         case 2: kern = TL == 8 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 2, 8, 3) : NEO_KW(SAMPLE_BY_PIECE, 2); break;
@@ -924,7 +934,6 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
         case 9: kern = NEO_KW(SAMPLE_ALL_PIECES, 9); break;
         case 10: kern = NEO_KW(SAMPLE_ALL_PIECES, 10); break;
 #endif
-        // 8-lane tiles: 12 warps per SM (168 registers, no spills); measured 33.1 vs 34.8 ms for 8 warps on config 4
         case 3: kern = TL == 8 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 3, 8, 3) : NEO_KW(SAMPLE_BY_PIECE, 3); break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
