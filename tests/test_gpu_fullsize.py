@@ -175,3 +175,42 @@ def test_config5_dense_map_10_pieces():
     conv = (out['ok'] == 1) & (out['status'] <= 1)
     ev = h.eval(M, out['x'][conv], head[conv], tail[conv])
     assert np.allclose(ev['costs'], out['costs'][conv], rtol=1e-9, atol=1e-12)
+
+
+def handle_with_env(cfg, n_maps, **env):
+    """A handle created under development switches (read once, at neo_create)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return lib.Handle(cfg, 0, n_maps)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize('M,tile', [(3, 8), (3, 32), (10, 32)])
+def test_grouped_starts_change_nothing(M, tile):
+    """The one-CTA-per-SM variant (warps start their evaluations in groups on named barriers) against the plain one:
+    identical outputs problem by problem, for batch sizes that leave most warps without work (1, 7), end inside a group
+    (37 problems) or fill several SMs (1500) -- the drain path of the ticket/barrier scheme is what these exercise."""
+    cfg = YamlConfig(); cfg.init_wpts_num = M - 1
+    w = make_world(3, dense=(M == 10))
+    for B in (1, 7, 37, 1500):
+        head, tail = make_problems(w, B, M=M, first=50 + B)
+        q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
+        rq, rts = guesses.retry_guesses(cfg, head, tail, M, 4, rng=np.random.default_rng(B))
+        outs = []
+        for grouped, group_warps in ((0, 0), (1, 9), (1, 12), (1, 2)):
+            env = dict(NEO_TILE=tile, NEO_GROUPED=grouped)
+            if group_warps:
+                env['NEO_GROUP_WARPS'] = group_warps
+            h = handle_with_env(cfg, 1, **env)
+            h.set_map_occupancy(0, w.H, w.W, w.res, w.ox, w.oy, w.occ)
+            outs.append(h.optimize(M, q0, ts0, lib.pad_state(head), lib.pad_state(tail), None, rq, rts, 5))
+            h.close()
+        for o in outs[1:]:
+            for k in ('x', 'ts', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):
+                assert np.array_equal(o[k], outs[0][k]), (B, k)
