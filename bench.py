@@ -568,7 +568,7 @@ def main():
                 'ok_fraction': acc['ok_fraction'], 'clocks': clocks, 'map_build_s': map_build_s,
                 'map_build_note': f"{len(wl['worlds'])} occupancy grids -> exact EDT + gradient on the device (neo_set_maps_occupancy: H2D, 5 kernels per map, one sync), outside the timed steps",
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
-                        'includes': 'neo_optimize with host buffers (H2D, kernel, D2H)' + (' + pack + NCCL all-gather of the records + D2H of the gathered batch' if distributed else '')},
+                        'includes': 'neo_optimize with host buffers: inputs staged in pinned memory and copied (retry guesses are read over PCIe on demand, counted in full here), kernel, results written by the kernel into mapped pinned memory, scatter into the caller arrays' + (' + pack + NCCL all-gather of the records + D2H of the gathered batch' if distributed else '')},
                 'gpu_launches': int(launches) * world_size,
                 'roofline': roofline_of(acc, M, step_ms, fp64_peak, hbm_peak, bool(peaks), hbm_bytes_of(wl), wl['name']),
                 'wall_s_timed_region': t_wall}

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -449,7 +450,6 @@ struct neo_handle {
     MapView *d_maps = nullptr;
     unsigned int *d_counter = nullptr;
     std::vector<DevBuf> bufs;        // reusable device staging buffers for the host-pointer entry points
-    std::vector<cudaEvent_t> part_done;    // neo_optimize: a part of the results has arrived in pinned memory
     DevBuf pinned;                   // reusable pinned host staging buffer (neo_optimize)
     DevBuf astar;                    // per-warp search scratch of neo_astar (node records all-zero between launches)
     size_t astar_cap = 0;            // cells per warp the scratch is laid out for
@@ -458,6 +458,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    bool host_timing = false;        // development switch (env NEO_HOST_TIMING): neo_optimize prints its host-side phases
     int grouped = -1, group_warps = 0;   // development switches (env NEO_GROUPED = 0 | 1, NEO_GROUP_WARPS at neo_create; -1 / 0: by batch size)
     int tile = 0;                    // development switch (env NEO_TILE = 8 | 16 | 32 at neo_create; 0: by batch size):
                                      // lanes per problem for M <= 4, see launch_optimize / include/neoopt.h
@@ -516,7 +517,7 @@ static int pin_buf(neo_handle *h, size_t bytes, void **out)
         if (b.p) CK(cudaFreeHost(b.p));
         b.p = nullptr; b.cap = 0;
         const size_t cap = bytes + bytes / 4 + 256;
-        CK(cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&b.p, cap, cudaHostAllocMapped));      // mapped: the optimizer writes its results straight into it
         b.cap = cap;
     }
     *out = b.p;
@@ -546,6 +547,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     }
     neo_handle *h = new neo_handle();
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps); h->views.resize(max_maps);
+    h->host_timing = getenv("NEO_HOST_TIMING") != nullptr;
     if (const char *e = getenv("NEO_GROUPED")) h->grouped = atoi(e) ? 1 : 0;
     if (const char *e = getenv("NEO_GROUP_WARPS")) h->group_warps = atoi(e);
     if (const char *e = getenv("NEO_TILE")) { const int t = atoi(e); h->tile = (t == 8 || t == 16 || t == 32) ? t : 0; }
@@ -577,7 +579,6 @@ extern "C" int neo_destroy(neo_handle *h)
     if (h->astar.p) cudaFree(h->astar.p);
     cudaFree(h->d_maps); cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    for (auto e : h->part_done) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
     return NEO_OK;
@@ -1181,9 +1182,10 @@ static void parallel_ranges(size_t count, F fn)
 }
 
 // Host-buffer entry: inputs are assembled in ONE pinned staging buffer that mirrors the device layout
-// (x0 = [q0, map_T2tau(ts0)], EP:207-211) in three stages, each copied while the next is assembled; results come back
-// in five parts, each scattered into the caller's arrays while the next is in flight. For large batches both host passes run on several threads (at 65,536 problems
-// they move 50 MB and take 196,608 logarithms -- a quarter of the kernel's time on one thread).
+// (x0 = [q0, map_T2tau(ts0)], EP:207-211) in three stages, each copied while the next is assembled; results are written
+// by the kernel straight into the same pinned buffer (mapped) and scattered into the caller's arrays once it ends. For
+// large batches both host passes run on several threads (at 65,536 problems they move 50 MB and take 196,608 logarithms
+// -- a quarter of the kernel's time on one thread).
 static int optimize_host(neo_handle *h, int B, int M, const double *q0, const double *ts0, const double *head,
                          const double *tail, const int32_t *map_ids, const double *retry_q, const double *retry_ts,
                          int max_attempts, neo_result *out, const TraceHost *trace)
@@ -1209,7 +1211,7 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
         size_t o = 0;
         auto off = [&](size_t bytes) { o = (o + 255) & ~(size_t)255; const size_t at = o; o += bytes; return at; };
         L.x0 = off(8 * b * n); L.head = off(8 * b * 6); L.tail = off(8 * b * 6); L.st0 = off(4 * b); L.ids = off(4 * b);
-        L.rq = off(8 * (b * A1 * nq + 1)); L.rtau = off(8 * NEO_MAX_PIECES); L.in_end = off(0);
+        L.rtau = off(8 * NEO_MAX_PIECES); L.in_end = off(0); L.rq = off(8 * (b * A1 * nq + 1));
         L.x = off(8 * b * n); L.ts = off(8 * b * M); L.coeffs = off(8 * b * N2); L.costs = off(8 * b * 4);
         L.status = off(4 * b); L.ok = off(4 * b); L.attempt = off(4 * b); L.nit = off(4 * b); L.runs = off(4 * b);
         L.nfev = off(4 * b); L.work = off(8 * b * 4); L.end = off(0);
@@ -1220,6 +1222,9 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
 
     double *hx0 = (double *)(hbase + L.x0);
     int32_t *hst = (int32_t *)(hbase + L.st0);
+    const bool timing = h->host_timing;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto t_begin = now();
     const neo_config cfg = h->cfg;
     std::atomic<int> any_bad_flag{0};
     // three stages, each copied to the device while the next one is assembled
@@ -1247,22 +1252,27 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
         memcpy(hbase + L.tail + 48 * i0, tail + i0 * 6, 48 * (i1 - i0));
         if (map_ids) memcpy(hbase + L.ids + 4 * i0, map_ids + i0, 4 * (i1 - i0));
     });
-    CK(cudaMemcpyAsync(dbase + L.head, hbase + L.head, L.rq - L.head, cudaMemcpyHostToDevice, st));     // head, tail, st0, ids
     double *rtau = (double *)(hbase + L.rtau);
     int rstatus = 0;
-    if (A1) {
+    if (A1)
         for (int k = 0; k < M; k++) { rtau[k] = 0.0; const int s1 = T2tau_one(&h->cfg, retry_ts[k], &rtau[k]); if (s1) rstatus = s1; }
+    CK(cudaMemcpyAsync(dbase + L.head, hbase + L.head, L.in_end - L.head, cudaMemcpyHostToDevice, st));     // head, tail, st0, ids, retry tau
+    // the retry guesses (the largest input: 4 per problem) stay in the pinned buffer: only the problems that do retry
+    // read theirs, through the mapped pointer, when the retry starts
+    if (A1)
         parallel_ranges(b, [&](size_t i0, size_t i1) {
             memcpy(hbase + L.rq + 8 * i0 * A1 * nq, retry_q + i0 * A1 * nq, 8 * (i1 - i0) * A1 * nq);
         });
-        CK(cudaMemcpyAsync(dbase + L.rq, hbase + L.rq, L.in_end - L.rq, cudaMemcpyHostToDevice, st));
-    }
+    // results: the kernel writes every resolved problem's record straight into the pinned staging buffer (mapped host
+    // memory; 0.46 KB per problem, spread over the whole launch), so no device-to-host copy follows the kernel
+    char *rbase = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&rbase, hbase, 0));
     neo_result d;
-    d.x = (double *)(dbase + L.x); d.ts = (double *)(dbase + L.ts); d.coeffs = (double *)(dbase + L.coeffs);
-    d.costs = (double *)(dbase + L.costs);
-    d.status = (int32_t *)(dbase + L.status); d.ok = (int32_t *)(dbase + L.ok); d.attempt = (int32_t *)(dbase + L.attempt);
-    d.nit = (int32_t *)(dbase + L.nit); d.runs = (int32_t *)(dbase + L.runs); d.nfev = (int32_t *)(dbase + L.nfev);
-    d.work = out->work ? (int64_t *)(dbase + L.work) : nullptr;
+    d.x = (double *)(rbase + L.x); d.ts = (double *)(rbase + L.ts); d.coeffs = (double *)(rbase + L.coeffs);
+    d.costs = (double *)(rbase + L.costs);
+    d.status = (int32_t *)(rbase + L.status); d.ok = (int32_t *)(rbase + L.ok); d.attempt = (int32_t *)(rbase + L.attempt);
+    d.nit = (int32_t *)(rbase + L.nit); d.runs = (int32_t *)(rbase + L.runs); d.nfev = (int32_t *)(rbase + L.nfev);
+    d.work = out->work ? (int64_t *)(rbase + L.work) : nullptr;
     TraceDev td;
     size_t tr_tasks = 0;
     if (trace) {      // test path: the per-task evaluation trace lives in its own device buffer
@@ -1279,10 +1289,11 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
         }
         CK(cudaMemsetAsync(td.len, 0, sizeof(int32_t) * tr_tasks, st));
     }
+    const auto t_staged = now();
     CK(cudaEventRecord(h->ev0, st));
     rc = optimize_dev_impl(h, B, M, (const double *)(dbase + L.x0), any_bad ? (const int32_t *)(dbase + L.st0) : nullptr,
                            (const double *)(dbase + L.head), (const double *)(dbase + L.tail),
-                           map_ids ? (const int32_t *)(dbase + L.ids) : nullptr, A1 ? (const double *)(dbase + L.rq) : nullptr,
+                           map_ids ? (const int32_t *)(dbase + L.ids) : nullptr, A1 ? (const double *)(rbase + L.rq) : nullptr,
                            A1 ? (const double *)(dbase + L.rtau) : nullptr, rstatus, max_attempts, &d, st, trace ? &td : nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, st));
@@ -1295,41 +1306,15 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
         CK(cudaMemcpyAsync(trace->status, td.status, 4 * tr_tasks * cap, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(trace->len, td.len, 4 * tr_tasks, cudaMemcpyDeviceToHost, st));
     }
-    // results: five device-to-host copies (x + ts, three thirds of the coefficients, the small fields); each part is
-    // scattered into the caller's arrays while the next one is in flight
-    while (h->part_done.size() < 5) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->part_done.push_back(e);
-    }
-    const size_t third = (b + 2) / 3;
-    const size_t c_lo[3] = {0, third < b ? third : b, 2 * third < b ? 2 * third : b}, c_hi[3] = {c_lo[1], c_lo[2], b};
-    CK(cudaMemcpyAsync(hbase + L.x, dbase + L.x, L.coeffs - L.x, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(h->part_done[0], st));
-    for (int k = 0; k < 3; k++) {
-        if (c_hi[k] > c_lo[k])
-            CK(cudaMemcpyAsync(hbase + L.coeffs + 8 * N2 * c_lo[k], dbase + L.coeffs + 8 * N2 * c_lo[k], 8 * N2 * (c_hi[k] - c_lo[k]),
-                               cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(h->part_done[1 + k], st));
-    }
-    CK(cudaMemcpyAsync(hbase + L.costs, dbase + L.costs, L.end - L.costs, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(h->part_done[4], st));
-    CK(cudaEventSynchronize(h->part_done[0]));
+    const auto t_launched = now();
+    CK(cudaStreamSynchronize(st));
+    const auto t_done = now();
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     parallel_ranges(b, [&](size_t i0, size_t i1) {
-        memcpy(out->x + i0 * n, hbase + L.x + 8 * i0 * n, 8 * (i1 - i0) * n);
-        memcpy(out->ts + i0 * M, hbase + L.ts + 8 * i0 * M, 8 * (i1 - i0) * M);
-    });
-    for (int k = 0; k < 3; k++) {
-        CK(cudaEventSynchronize(h->part_done[1 + k]));
-        const size_t lo = c_lo[k];
-        parallel_ranges(c_hi[k] - lo, [&](size_t i0, size_t i1) {
-            memcpy(out->coeffs + (lo + i0) * N2, hbase + L.coeffs + 8 * (lo + i0) * N2, 8 * (i1 - i0) * N2);
-        });
-    }
-    CK(cudaStreamSynchronize(st));
-    parallel_ranges(b, [&](size_t i0, size_t i1) {
         const size_t c = i1 - i0;
+        memcpy(out->x + i0 * n, hbase + L.x + 8 * i0 * n, 8 * c * n);
+        memcpy(out->ts + i0 * M, hbase + L.ts + 8 * i0 * M, 8 * c * M);
+        memcpy(out->coeffs + i0 * N2, hbase + L.coeffs + 8 * i0 * N2, 8 * c * N2);
         memcpy(out->costs + i0 * 4, hbase + L.costs + 32 * i0, 32 * c);
         memcpy(out->status + i0, hbase + L.status + 4 * i0, 4 * c);
         memcpy(out->ok + i0, hbase + L.ok + 4 * i0, 4 * c);
@@ -1339,6 +1324,11 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
         memcpy(out->nfev + i0, hbase + L.nfev + 4 * i0, 4 * c);
         if (out->work) memcpy(out->work + i0 * 4, hbase + L.work + 32 * i0, 32 * c);
     });
+    if (timing) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+        fprintf(stderr, "neo_optimize B=%d: stage inputs %.3f ms, launch %.3f ms, wait %.3f ms (kernel %.3f ms), scatter %.3f ms\n", B,
+                ms(t_begin, t_staged), ms(t_staged, t_launched), ms(t_launched, t_done), h->last_ms, ms(t_done, now()));
+    }
     return NEO_OK;
 }
 

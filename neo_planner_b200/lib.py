@@ -108,6 +108,8 @@ def pad_state(s):
     s = np.asarray(s, dtype=np.float64)
     if s.shape[-1] != 2:
         raise ValueError('only planar problems (D = 2) are supported, as in the reference node (NODE:593-595)')
+    if s.ndim >= 2 and s.shape[-2] == 3 and s.flags.c_contiguous:
+        return s                               # already padded: no copy (3 MB per call at 65,536 problems)
     out = np.zeros(s.shape[:-2] + (3, 2))
     k = min(3, s.shape[-2])
     out[..., :k, :] = s[..., :k, :]
