@@ -166,7 +166,14 @@ __host__ __device__ inline int tile_mem_doubles(int M, int TL = 32, bool one_blo
     return (tot + 1) & ~1;
 }
 
-__device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block = false)
+// evaluator only (k_eval, k_coeffs): no optimizer state behind the scratch regions
+__host__ __device__ inline int eval_mem_doubles(int M, int TL = 32, bool one_block = false)
+{
+    const int tot = 12 + scratch_a_doubles(M) + scratch_b_doubles(M, TL, one_block) + (M > 4 ? 2 * M + M + 32 : 0);
+    return (tot + 1) & ~1;
+}
+
+__device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block = false, bool eval_only = false)
 {
     const int n = 3 * M - 2, M1 = M + 1;
     TileMem m;
@@ -191,6 +198,12 @@ __device__ inline TileMem carve(double *base, int M, int TL = 32, bool one_block
     m.lam = m.r + 4 * M1;
     m.h = m.lam + 4 * M1;
     m.Gs = m.h + 12 * M;
+    if (eval_only) {
+        base = scratch + scratch_a_doubles(M) + scratch_b_doubles(M, TL, one_block);
+        m.ws = m.wy = m.yr = m.rzd = m.dr = m.gv = m.dv = m.ls = m.oc = nullptr;
+        m.lw = base; m.nsprev = base + 2 * M; m.asg = base + 3 * M;
+        return m;
+    }
     base = scratch + scratch_doubles(M, TL, one_block);
     m.ws = base; base += HIST * n;
     m.wy = base; base += HIST * n;

@@ -316,7 +316,7 @@ struct EvalArgs {
 
 // get_cost + get_grad (EP:539-585) fused, one tile per problem
 template <int MODE, int MC, int TL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, const EvalArgs a)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_eval(const DevParams P, const EvalArgs a)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_eval(const DevParams P, 
     constexpr int TPW = 32 / TL, TPC = WARPS_PER_CTA * TPW;
     const int M = MC > 0 ? MC : a.M, n = 3 * M - 2, N = 6 * M;
     const int tile = warp * TPW + lane / TL;
-    const TileMem m = carve(smem + (size_t)tile * tile_mem_doubles(M, TL), M, TL);
+    constexpr bool ONE_BLOCK = MODE == SAMPLE_BY_PIECE_STAGED;
+    const TileMem m = carve(smem + (size_t)tile * eval_mem_doubles(M, TL, ONE_BLOCK), M, TL, ONE_BLOCK, true);
     for (size_t b = (size_t)blockIdx.x * TPC + tile; b < (size_t)a.B; b += (size_t)gridDim.x * TPC) {
         begin_problem(T, m, M, a.head + b * 6, a.tail + b * 6);
         const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
@@ -974,8 +975,8 @@ static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
     const int TL = tile_lanes(h, a.B, a.M);
     switch (a.M) {
 #ifndef NEO_FAST_BUILD
-        case 2: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 2, 8> : k_eval<SAMPLE_BY_PIECE, 2, 32>; break;
-        case 4: kern = TL == 16 ? k_eval<SAMPLE_BY_PIECE, 4, 16> : k_eval<SAMPLE_BY_PIECE, 4, 32>; break;
+        case 2: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE_STAGED, 2, 8> : k_eval<SAMPLE_BY_PIECE, 2, 32>; break;
+        case 4: kern = TL == 16 ? k_eval<SAMPLE_BY_PIECE_STAGED, 4, 16> : k_eval<SAMPLE_BY_PIECE, 4, 32>; break;
         case 5: kern = k_eval<SAMPLE_ALL_PIECES, 5, 32>; break;
         case 6: kern = k_eval<SAMPLE_ALL_PIECES, 6, 32>; break;
         case 7: kern = k_eval<SAMPLE_ALL_PIECES, 7, 32>; break;
@@ -983,10 +984,11 @@ static int launch_eval(neo_handle *h, EvalArgs a, cudaStream_t st)
         case 9: kern = k_eval<SAMPLE_ALL_PIECES, 9, 32>; break;
         case 10: kern = k_eval<SAMPLE_ALL_PIECES, 10, 32>; break;
 #endif
-        case 3: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE, 3, 8> : k_eval<SAMPLE_BY_PIECE, 3, 32>; break;
+        case 3: kern = TL == 8 ? k_eval<SAMPLE_BY_PIECE_STAGED, 3, 8> : k_eval<SAMPLE_BY_PIECE, 3, 32>; break;
         default: return fail(h, "M must be in [2, NEO_MAX_PIECES]");
     }
-    const size_t smem = smem_bytes(a.M, TL);
+    // evaluator-only shared memory (no optimizer state): half of k_optimize's per tile, so registers decide the occupancy
+    const size_t smem = sizeof(double) * (size_t)eval_mem_doubles(a.M, TL, TL < 32) * WARPS_PER_CTA * (32 / TL);
     int rc = prep_kernel(h, kern, smem, &occ);
     if (rc) return rc;
     const int per_cta = WARPS_PER_CTA * (32 / TL);
