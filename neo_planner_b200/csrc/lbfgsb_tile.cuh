@@ -31,7 +31,6 @@ namespace neo {
 // Development probe (-DNEO_OPT_TICKS, devtools/README.md): cycles spent in each phase of the optimizer, summed over all
 // tiles by their first lane. Compiled out of the shipped library.
 #ifdef NEO_OPT_TICKS
-__device__ long long g_opt_ticks[64];
 #define OT_BEGIN long long ot_last = clock64()
 #define OT(i) do { const long long ot_now = clock64(); if (T.tl == 0) { atomicAdd((unsigned long long *)&g_opt_ticks[i], (unsigned long long)(ot_now - ot_last)); atomicAdd((unsigned long long *)&g_opt_ticks[32 + (i)], 1ull); } ot_last = clock64(); } while (0)
 #else

@@ -31,14 +31,20 @@
 #include "dd_exp.h"
 
 namespace neo {
+#ifdef NEO_OPT_TICKS
+__device__ long long g_opt_ticks[64];      // development probe: cycles [0..32) and calls [32..64) per phase
+#endif
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// Phase timestamps for the development latency probe (k_eval_ticks in neoopt.cu); compiled out everywhere else.
-#ifdef NEO_TICKS
-#define NEO_TICK(i) do { T.sync(); if (ticks) ticks[i] = clock64(); } while (0)
+// Phase cycles of the evaluator for the development probe (-DNEO_OPT_TICKS, scripts/gpu_opt_ticks.py: counters 17..25 of
+// g_opt_ticks, summed over tiles by their first lane); compiled out everywhere else.
+#ifdef NEO_OPT_TICKS
+#define NEO_TICK(i) do { const long long et_now = clock64(); if ((i) > 0 && T.tl == 0) { atomicAdd((unsigned long long *)&g_opt_ticks[16 + (i)], (unsigned long long)(et_now - et_last)); atomicAdd((unsigned long long *)&g_opt_ticks[48 + (i)], 1ull); } et_last = clock64(); } while (0)
+#define NEO_TICK_DECL long long et_last = 0
 #else
 #define NEO_TICK(i) do { } while (0)
+#define NEO_TICK_DECL do { } while (0)
 #endif
 constexpr int HIST = 10;        // L-BFGS memory (maxcor, EP:220)
 constexpr int LBW = 2 * HIST;   // order of the middle matrix of the compact representation
@@ -465,6 +471,7 @@ __device__ __forceinline__ void eval_fg(const Tile<TL> &T, const DevParams &P, c
 {
     static_assert(MODE != SAMPLE_ALL_PIECES || TL == 32, "the all-pieces schedule assigns the 32 lanes of a warp");
     const int lane = T.tl;
+    NEO_TICK_DECL;
     NEO_TICK(0);
     const int nq = 2 * (M - 1);
     out.status = 0; out.ns = out.nv = out.nc = 0;
