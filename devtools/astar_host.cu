@@ -27,19 +27,28 @@ extern "C" int sim_astar(int H, int W, double res, double ox, double oy, const d
     map.blocked = blocked.data();
     std::vector<neo::AstarNode> nodes(cap);
     memset(nodes.data(), 0, sizeof(neo::AstarNode) * cap);
-    std::vector<int> order(cap);
+    std::vector<int> order(cap + neo::ASTAR_ORDER_SLACK);
     std::vector<neo::OpenRec> spill(cap);
+    // like k_astar: a first pass with room for `icap` inserted nodes (env NEO_ASTAR_ICAP; default: the whole grid), and a
+    // second one with full-size lists for the searches that outgrow it
+    size_t icap = cap;
+    if (const char *e = getenv("NEO_ASTAR_ICAP")) { const long v = atol(e); if (v > 0 && (size_t)v < cap) icap = (size_t)v; }
     std::vector<double> f(open_fast), g(open_fast);
     std::vector<int> xy(open_fast), tag(open_fast);
     neo::OpenList ol;
     ol.f = f.data(); ol.g = g.data(); ol.xy = xy.data(); ol.tag = tag.data(); ol.cap = open_fast; ol.spill = spill.data();
     for (int b = 0; b < B; b++) {
-        neo::astar_problem(map, nodes.data(), order.data(), ol, start + 2 * b, target + 2 * b, max_closed, max_path,
-                           path ? path + (size_t)b * max_path * 2 : nullptr, path_len + b, pruned + 8 * b, status + b,
-                           closed + b);
+        for (int pass = 0; pass < 2; pass++) {
+            const bool done = neo::astar_problem(map, nodes.data(), order.data(), ol, (int)(pass ? cap : icap), start + 2 * b,
+                                                 target + 2 * b, max_closed, max_path,
+                                                 path ? path + (size_t)b * max_path * 2 : nullptr, path_len + b,
+                                                 pruned + 8 * b, status + b, closed + b);
+            if (done) break;
+            if (pass == 1) return 2;
+        }
     }
     // the scratch must come back clean
     for (size_t i = 0; i < cap; i++)
-        if (nodes[i].state != 0 || nodes[i].parent != 0) return 1;
+        if (nodes[i] != 0u) return 1;
     return 0;
 }

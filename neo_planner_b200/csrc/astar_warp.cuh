@@ -9,10 +9,12 @@
 //
 // The open list {f, g, cell, insertion number} lives in shared memory (512 entries per warp, structure of arrays; longer
 // lists spill to HBM), so the scan of every step reads on-chip data only and f is computed once per insertion/update.
-// Per-warp scratch in HBM (dense over the enlarged grid, 36 B per cell): node records {parent, state/open position}, the
-// insertion list (used to wipe exactly the touched records afterwards and, later, as the key-node list) and the spill
-// area of the open list. With 400 x 400 search cells that is 5.8 MB per warp, of which one search touches a few thousand
-// records.
+// Per-warp scratch in HBM: ONE 4-byte node record per cell of the enlarged grid {move that led here, state/open position}
+// (dense: the search indexes it by cell), plus an insertion list (used to wipe exactly the touched records afterwards
+// and, later, as the key-node list) and the spill area of the open list, both sized for `icap` inserted nodes (28 B
+// each), not for the grid: one search touches a few thousand records. With 400 x 400 search cells that is 0.64 + 0.46 MB
+// per warp (round 1: 5.8 MB). A search that inserts more than icap nodes stops, reports ASTAR_OVERFLOW to the kernel and
+// is re-run by the second pass with full-size lists on a few warps (k_astar, pass 1).
 //
 // The same source runs with a single lane on the host (devtools/astar_host.cu) -- a development aid used to check the
 // logic against oracle/astar_ref.py in the GPU-less build container; the library never calls it.
@@ -25,10 +27,21 @@
 
 namespace neo {
 
-struct AstarNode {
-    int parent;     // grid index of the parent, -1 for the start (AP:16)
-    int state;      // 0 untouched, -1 closed (AP:72-73), k + 1: open, stored at position k of the open list
-};
+#define NEO_HD_DECL __host__ __device__ __forceinline__
+
+// Node record: bits 0..3 = the move that led to this node (0..7, index into the move table; 8 = start node, AP:16: the
+// parent is this cell minus that move), bits 4..31 = state: 0 untouched, 1 closed (AP:72-73), k + 2: open, stored at
+// position k of the open list.
+typedef unsigned int AstarNode;
+constexpr unsigned ASTAR_CLOSED = 1u;
+NEO_HD_DECL unsigned an_state(AstarNode n) { return n >> 4; }
+NEO_HD_DECL unsigned an_move(AstarNode n) { return n & 15u; }
+NEO_HD_DECL AstarNode an_make(unsigned state, unsigned move) { return (state << 4) | move; }
+// moves (1,0) (0,1) (-1,0) (0,-1) (-1,-1) (-1,1) (1,-1) (1,1): (d + 1) packed two bits per move
+NEO_HD_DECL int an_dx(unsigned mv) { return (int)((0xA046u >> (2 * mv)) & 3u) - 1; }
+NEO_HD_DECL int an_dy(unsigned mv) { return (int)((0x8819u >> (2 * mv)) & 3u) - 1; }
+// grid index of the parent of cell `idx` (row length W), -1 for the start node
+NEO_HD_DECL int an_parent(AstarNode n, int idx, int W) { const unsigned mv = an_move(n); return mv >= 8u ? -1 : idx - an_dx(mv) - an_dy(mv) * W; }
 
 // One open node (AP:55 `open_set`). f = g + hypot is kept up to date with g, so the scan for the minimum reads f and, on
 // ties, the insertion number only.
@@ -46,7 +59,7 @@ struct OpenList {
     OpenRec *spill;
 };
 
-enum { ASTAR_FOUND = 0, ASTAR_EXHAUSTED = 1, ASTAR_START_OUTSIDE = 2, ASTAR_LIMIT = 3 };
+enum { ASTAR_FOUND = 0, ASTAR_EXHAUSTED = 1, ASTAR_START_OUTSIDE = 2, ASTAR_LIMIT = 3, ASTAR_OVERFLOW = 100 /* internal */ };
 
 #define NEO_HD __host__ __device__ __forceinline__
 
@@ -230,9 +243,11 @@ NEO_HD void ol_put(const OpenList &o, int k, const OpenRec &r)
 }
 
 // One start/target pair, executed by one warp (all lanes call with the same arguments).
-//   nodes/order/ol.spill: this warp's scratch in HBM; nodes all-zero on entry and restored to all-zero on exit.
+//   nodes/order/ol.spill: this warp's scratch in HBM; nodes all-zero on entry and restored to all-zero on exit;
+//   order and ol.spill hold icap entries (+8 ints of slack in order).
 //   path_out (max_path, 2) may be NULL; path_len is the full length even when it exceeds max_path.
-NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const OpenList ol, const double *start,
+// Returns false (outputs untouched, scratch clean) when the search inserted more than icap nodes.
+NEO_HD bool astar_problem(const MapView map, AstarNode *nodes, int *order, const OpenList ol, int icap, const double *start,
                           const double *target, int max_closed, int max_path, double *path_out, int32_t *path_len_out,
                           double *pruned_out, int32_t *status_out, int32_t *closed_out)
 {
@@ -260,8 +275,7 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const
         if (lane == 0) {
             OpenRec r; r.g = 0.0; r.f = a_add(0.0, NEO_HYPOT(sx, sy)); r.xy = sx | (sy << 16); r.tag = 1;
             ol_put(ol, 0, r);
-            AstarNode s; s.parent = -1; s.state = 1;
-            nodes[s_idx] = s; order[0] = s_idx;
+            nodes[s_idx] = an_make(2u, 8u); order[0] = s_idx;
         }
         n_open = 1; n_seen = 1;
         a_sync();
@@ -284,12 +298,17 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const
             const int cx = cur_rec.xy & 0xffff, cy = cur_rec.xy >> 16;
             const int cur = cx + cy * g.W;
             const double cg = cur_rec.g;
-            if (cx == tx && cy == ty) { t_parent = nodes[cur].parent; break; }  // AP:66-69
+            if (cx == tx && cy == ty) { t_parent = an_parent(nodes[cur], cur, g.W); break; }  // AP:66-69
             a_sync();
             if (lane == 0) {                                                     // AP:72-73
                 const int last = n_open - 1;
-                if (bk != last) { const OpenRec mv = ol_get(ol, last); ol_put(ol, bk, mv); nodes[(mv.xy & 0xffff) + (mv.xy >> 16) * g.W].state = bk + 1; }
-                nodes[cur].state = -1;
+                if (bk != last) {
+                    const OpenRec mv = ol_get(ol, last);
+                    ol_put(ol, bk, mv);
+                    AstarNode &moved = nodes[(mv.xy & 0xffff) + (mv.xy >> 16) * g.W];
+                    moved = an_make((unsigned)bk + 2u, an_move(moved));
+                }
+                nodes[cur] = an_make(ASTAR_CLOSED, an_move(nodes[cur]));
             }
             n_open--; n_closed++;
             a_sync();
@@ -299,35 +318,35 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const
                 const int mv = base + lane;
                 bool fresh = false; int nidx = 0, nxy = 0; double ng = 0.0, nf = 0.0;
                 if (mv < 8) {
-                    // moves (1,0) (0,1) (-1,0) (0,-1) (-1,-1) (-1,1) (1,-1) (1,1): (d + 1) packed two bits per move
-                    const int nx = cx + (int)((0xA046u >> (2 * mv)) & 3u) - 1;
-                    const int ny = cy + (int)((0x8819u >> (2 * mv)) & 3u) - 1;
+                    const int nx = cx + an_dx((unsigned)mv), ny = cy + an_dy((unsigned)mv);
                     if (nx >= 0 && nx < g.W && ny >= 0 && ny < g.H) {
                         nidx = nx + ny * g.W; nxy = nx | (ny << 16);
                         const AstarNode c = nodes[nidx];
                         const bool blk = map.blocked[nidx] != 0;                      // has_collision at this node
-                        if (c.state >= 0 && !blk) {                                   // AP:83, AP:86
+                        if (an_state(c) != ASTAR_CLOSED && !blk) {                    // AP:83, AP:86
                             ng = a_add(cg, mv < 4 ? 1.0 : SQRT2);
                             nf = a_add(ng, NEO_HYPOT(nx, ny));
-                            if (c.state == 0) fresh = true;                           // AP:91-92
+                            if (an_state(c) == 0u) fresh = true;                      // AP:91-92
                             else {                                                    // AP:94-95
-                                OpenRec r = ol_get(ol, c.state - 1);
-                                if (r.g > ng) { r.g = ng; r.f = nf; ol_put(ol, c.state - 1, r); nodes[nidx].parent = cur; }
+                                const int pos = (int)an_state(c) - 2;
+                                OpenRec r = ol_get(ol, pos);
+                                if (r.g > ng) { r.g = ng; r.f = nf; ol_put(ol, pos, r); nodes[nidx] = an_make(an_state(c), (unsigned)mv); }
                             }
                         }
                     }
                 }
                 const unsigned b = a_ballot(fresh);
+                if (n_seen + a_popc(b) > icap) { status = ASTAR_OVERFLOW; break; }     // the lists are full: second pass
                 if (fresh) {
                     const int r = a_popc(b & lt);
                     OpenRec nr; nr.f = nf; nr.g = ng; nr.xy = nxy; nr.tag = n_seen + r + 1;
                     ol_put(ol, n_open + r, nr);
-                    AstarNode nn; nn.parent = cur; nn.state = n_open + r + 1;
-                    nodes[nidx] = nn; order[n_seen + r] = nidx;
+                    nodes[nidx] = an_make((unsigned)(n_open + r) + 2u, (unsigned)mv); order[n_seen + r] = nidx;
                 }
                 n_open += a_popc(b); n_seen += a_popc(b);
             }
             a_sync();
+            if (status == ASTAR_OVERFLOW) break;
         }
     }
 #undef NEO_HYPOT
@@ -337,11 +356,12 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const
     int n_chain = 0;
     if (status == ASTAR_FOUND && lane == 0) {
         int p = t_parent;
-        while (p != -1) { chain[n_chain++] = p; p = nodes[p].parent; }
+        while (p != -1) { chain[n_chain++] = p; p = an_parent(nodes[p], p, g.W); }
     }
     n_chain = a_from_lane0(n_chain);
     a_sync();
-    for (int k = lane; k < n_seen; k += NL) { AstarNode z; z.parent = 0; z.state = 0; nodes[order[k]] = z; }
+    for (int k = lane; k < n_seen; k += NL) nodes[order[k]] = 0u;
+    if (status == ASTAR_OVERFLOW) { a_sync(); return false; }
     const int L = (status == ASTAR_FOUND || status == ASTAR_EXHAUSTED) ? n_chain + 1 : 0;
 
 #define NEO_PATH_XY(i, X, Y)                                                                              \
@@ -419,6 +439,7 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const
     }
 #undef NEO_PATH_XY
     a_sync();
+    return true;
 }
 
 #ifdef __CUDACC__
@@ -426,7 +447,8 @@ NEO_HD void astar_problem(const MapView map, AstarNode *nodes, int *order, const
 constexpr int ASTAR_OPEN_FAST = 512;     // open-list positions per warp held in shared memory (24 B each)
 constexpr int ASTAR_WARPS_PER_CTA = 4;
 constexpr size_t ASTAR_SMEM_BYTES = (size_t)ASTAR_WARPS_PER_CTA * ASTAR_OPEN_FAST * 24;
-constexpr size_t ASTAR_BYTES_PER_CELL = sizeof(AstarNode) + sizeof(int) + sizeof(OpenRec);
+constexpr size_t ASTAR_BYTES_PER_INSERT = sizeof(int) + sizeof(OpenRec);      // insertion list + open-list spill
+constexpr int ASTAR_ORDER_SLACK = 8;
 
 struct AstarArgs {
     const MapView *maps;
@@ -436,9 +458,14 @@ struct AstarArgs {
     double *path;                // (B,max_path,2) or NULL
     int32_t *path_len, *status, *closed;
     double *pruned;              // (B,4,2)
-    AstarNode *nodes; int *order; OpenRec *spill;     // per-warp blocks of `cap` entries each
-    size_t cap;                  // scratch cells per warp
-    unsigned int *counter;
+    AstarNode *nodes;            // per-warp blocks of `cap` node records
+    int *order; OpenRec *spill;  // per-warp blocks of icap (+ slack) entries
+    size_t cap;                  // cells of the largest enlarged grid
+    int icap;                    // inserted nodes a search may reach in this pass
+    unsigned int *counter;       // work queue
+    int32_t *overflow;           // pass 0: problems whose search outgrew icap (count in overflow_count); pass 1: the work list
+    unsigned int *overflow_count;
+    int pass;
 };
 
 // one thread per node of the enlarged grid (map.blocked itself is not read)
@@ -459,18 +486,25 @@ __global__ void __launch_bounds__(ASTAR_WARPS_PER_CTA * 32) k_astar(const AstarA
     ol.g = ol.f + ASTAR_OPEN_FAST;
     ol.xy = (int *)((double *)astar_smem + (size_t)ASTAR_WARPS_PER_CTA * 2 * ASTAR_OPEN_FAST) + (size_t)wc * 2 * ASTAR_OPEN_FAST;
     ol.tag = ol.xy + ASTAR_OPEN_FAST;
-    ol.spill = a.spill + (size_t)warp * a.cap;
+    ol.spill = a.spill + (size_t)warp * a.icap;
     AstarNode *nodes = a.nodes + (size_t)warp * a.cap;
-    int *order = a.order + (size_t)warp * a.cap;
+    int *order = a.order + (size_t)warp * ((size_t)a.icap + ASTAR_ORDER_SLACK);
+    // pass 0: every problem, lists of icap entries; pass 1: the problems pass 0 could not finish, full-size lists
+    const unsigned total = a.pass ? *a.overflow_count : (unsigned)a.B;
     for (;;) {
-        unsigned int b = 0;
-        if (lane == 0) b = atomicAdd(a.counter, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= (unsigned)a.B) break;
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(a.counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= total) break;
+        const unsigned b = a.pass ? (unsigned)a.overflow[q] : q;
         const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
-        astar_problem(map, nodes, order, ol, a.start + 2 * (size_t)b, a.target + 2 * (size_t)b, a.max_closed, a.max_path,
-                      a.path ? a.path + (size_t)b * a.max_path * 2 : nullptr, a.path_len + b, a.pruned + 8 * (size_t)b,
-                      a.status + b, a.closed + b);
+        const bool done = astar_problem(map, nodes, order, ol, a.icap, a.start + 2 * (size_t)b, a.target + 2 * (size_t)b,
+                                        a.max_closed, a.max_path, a.path ? a.path + (size_t)b * a.max_path * 2 : nullptr,
+                                        a.path_len + b, a.pruned + 8 * (size_t)b, a.status + b, a.closed + b);
+        if (!done && lane == 0) {
+            if (a.pass == 0) a.overflow[atomicAdd(a.overflow_count, 1u)] = (int32_t)b;
+            else { a.path_len[b] = 0; a.status[b] = ASTAR_LIMIT; a.closed[b] = 0; }      // cannot happen: icap = cap in pass 1
+        }
     }
 }
 #endif

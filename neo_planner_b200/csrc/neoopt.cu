@@ -455,6 +455,8 @@ struct neo_handle {
     DevBuf astar;                    // per-warp search scratch of neo_astar (node records all-zero between launches)
     size_t astar_cap = 0;            // cells per warp the scratch is laid out for
     int astar_warps = 0;             // worker warps the scratch is laid out for
+    size_t astar_laid_icap = 0;      // inserted nodes per search the first-pass lists are laid out for
+    int astar_icap = 0;              // development switch (env NEO_ASTAR_ICAP at neo_create): first-pass list length, 0 = default
     std::string err;
     std::mutex mu;
     float last_ms = 0.f;
@@ -549,6 +551,7 @@ extern "C" int neo_create(const neo_config *cfg, int device, int max_maps, neo_h
     neo_handle *h = new neo_handle();
     h->device = device; h->cfg = *cfg; h->slots.resize(max_maps); h->views.resize(max_maps);
     h->host_timing = getenv("NEO_HOST_TIMING") != nullptr;
+    if (const char *e = getenv("NEO_ASTAR_ICAP")) h->astar_icap = atoi(e);
     if (const char *e = getenv("NEO_GROUPED")) h->grouped = atoi(e) ? 1 : 0;
     if (const char *e = getenv("NEO_GROUP_WARPS")) h->group_warps = atoi(e);
     if (const char *e = getenv("NEO_TILE")) { const int t = atoi(e); h->tile = (t == 8 || t == 16 || t == 32) ? t : 0; }
@@ -1432,12 +1435,15 @@ extern "C" int neo_sample(neo_handle *h, int B, int M, const double *coeffs, con
 // ---------------------------------------------------------------------------------------------------------
 constexpr size_t ASTAR_SCRATCH_BUDGET = (size_t)8 << 30;     // bytes of HBM the per-warp search scratch may take
 constexpr int ASTAR_WARPS_PER_SM = 16;
+constexpr int ASTAR_INSERT_CAP = 16384;       // inserted nodes per search the first pass has room for (28 B each)
+constexpr int ASTAR_PASS1_WARPS = 16;         // warps of the second pass (full-size lists: 28 B per grid cell each)
 
 static int astar_launch(neo_handle *h, int B, const double *start, const double *target, const int32_t *map_ids,
                         int max_closed, int max_path, double *path, int32_t *path_len, double *pruned, int32_t *status,
                         int32_t *closed, cudaStream_t st)
 {
-    // scratch: one dense block per worker warp, sized for the largest enlarged grid among the uploaded maps
+    // scratch per worker warp: one 4-byte node record per cell of the largest enlarged grid among the uploaded maps, and
+    // insertion list + open-list spill for icap inserted nodes; a few warps of the second pass get full-size lists
     size_t cap = 0;
     for (auto &s : h->slots)
         if (s.cells) { const size_t c = astar_grid_cells(s.H, s.W, s.res); cap = c > cap ? c : cap; }
@@ -1445,35 +1451,63 @@ static int astar_launch(neo_handle *h, int B, const double *start, const double 
     for (auto &s : h->slots)
         if (s.cells && (s.W + (int)(10.0 / s.res) > 0xffff || s.H + (int)(10.0 / s.res) > 0x7fff))
             return fail(h, "neo_astar: search grid too large (node coordinates are packed into 16 bits)");
-    const size_t per_warp = cap * ASTAR_BYTES_PER_CELL;
-    if (per_warp > ASTAR_SCRATCH_BUDGET) return fail(h, "neo_astar: search grid too large for the per-warp scratch budget");
+    if (cap >= ((size_t)1 << 27)) return fail(h, "neo_astar: search grid too large (open positions are packed into 28 bits)");
+    size_t icap = h->astar_icap > 0 ? (size_t)h->astar_icap : (size_t)ASTAR_INSERT_CAP;
+    if (icap > cap) icap = cap;
+    const size_t list0 = ASTAR_BYTES_PER_INSERT * icap + sizeof(int) * ASTAR_ORDER_SLACK;
+    const size_t list1 = ASTAR_BYTES_PER_INSERT * cap + sizeof(int) * ASTAR_ORDER_SLACK;
+    const size_t per_warp = sizeof(AstarNode) * cap + list0;
+    size_t warps1 = ASTAR_PASS1_WARPS;
+    if (list1 * warps1 > ASTAR_SCRATCH_BUDGET / 4) warps1 = ASTAR_SCRATCH_BUDGET / 4 / list1;
+    warps1 = warps1 / ASTAR_WARPS_PER_CTA * ASTAR_WARPS_PER_CTA;
+    if (warps1 < (size_t)ASTAR_WARPS_PER_CTA) warps1 = ASTAR_WARPS_PER_CTA;
+    const size_t budget0 = ASTAR_SCRATCH_BUDGET - list1 * warps1;
+    if (per_warp * ASTAR_WARPS_PER_CTA > budget0) return fail(h, "neo_astar: search grid too large for the scratch budget");
     size_t warps = (size_t)h->sm_count * ASTAR_WARPS_PER_SM;
-    if (warps > ASTAR_SCRATCH_BUDGET / per_warp) warps = ASTAR_SCRATCH_BUDGET / per_warp;
+    if (warps > budget0 / per_warp) warps = budget0 / per_warp;
     if (warps > (size_t)B) warps = B;
     if (warps < 1) warps = 1;
     warps = (warps + ASTAR_WARPS_PER_CTA - 1) / ASTAR_WARPS_PER_CTA * ASTAR_WARPS_PER_CTA;     // whole CTAs
-    if (h->astar_cap != cap || (size_t)h->astar_warps < warps) {
+    if (warps < warps1) warps = warps1;                                                         // pass 1 borrows node blocks
+    if (h->astar_cap != cap || (size_t)h->astar_warps < warps || h->astar_laid_icap != icap) {
         if (h->astar.p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(h->astar.p)); h->astar.p = nullptr; }
         h->astar_cap = 0; h->astar_warps = 0;
-        CK(cudaMalloc(&h->astar.p, per_warp * warps));
-        CK(cudaMemsetAsync((char *)h->astar.p + sizeof(OpenRec) * cap * warps, 0, sizeof(AstarNode) * cap * warps, st));   // nodes untouched
+        CK(cudaMalloc(&h->astar.p, per_warp * warps + list1 * warps1));
+        CK(cudaMemsetAsync(h->astar.p, 0, sizeof(AstarNode) * cap * warps, st));   // nodes untouched
         CK(cudaFuncSetAttribute(k_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASTAR_SMEM_BYTES));
-        h->astar_cap = cap; h->astar_warps = (int)warps;
+        h->astar_cap = cap; h->astar_warps = (int)warps; h->astar_laid_icap = icap;
     }
+    int rc;
+    int32_t *overflow;
+    if ((rc = dev_buf(h, 9, sizeof(int32_t) * (size_t)B + 256, (void **)&overflow))) return rc;
     AstarArgs a;
     a.maps = h->d_maps; a.map_ids = map_ids; a.start = start; a.target = target;
     a.B = B; a.max_closed = max_closed; a.max_path = max_path;
     a.path = path; a.path_len = path_len; a.status = status; a.closed = closed; a.pruned = pruned;
     const size_t laid = (size_t)h->astar_warps;                 // the layout follows the allocation, not this launch
-    a.spill = (OpenRec *)h->astar.p;                            // 24-B records first (8-byte aligned), then nodes, then ints
-    a.nodes = (AstarNode *)((char *)h->astar.p + sizeof(OpenRec) * cap * laid);
-    a.order = (int *)((char *)a.nodes + sizeof(AstarNode) * cap * laid);
+    // [nodes: laid x cap x 4 B][pass 0: spill laid x icap x 24 B | order laid x (icap + 8) x 4 B][pass 1: spill | order]
+    char *p0 = (char *)h->astar.p + sizeof(AstarNode) * cap * laid;
+    char *p1 = p0 + list0 * laid;
+    a.nodes = (AstarNode *)h->astar.p;
     a.cap = cap;
-    a.counter = h->d_counter + 16;
-    CK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+    a.overflow = overflow;
+    a.overflow_count = h->d_counter + 18;
+    CK(cudaMemsetAsync(h->d_counter + 16, 0, 3 * sizeof(unsigned int), st));
+    // pass 0
+    a.spill = (OpenRec *)p0; a.order = (int *)(p0 + sizeof(OpenRec) * icap * laid);
+    a.icap = (int)icap; a.pass = 0; a.counter = h->d_counter + 16;
     k_astar<<<(unsigned)(warps / ASTAR_WARPS_PER_CTA), ASTAR_WARPS_PER_CTA * 32, ASTAR_SMEM_BYTES, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
+    // pass 1: searches that inserted more than icap nodes, on a few warps with lists as long as the grid (usually none:
+    // the kernel reads the count on the device and returns)
+    if (icap < cap) {
+        a.spill = (OpenRec *)p1; a.order = (int *)(p1 + sizeof(OpenRec) * cap * warps1);
+        a.icap = (int)cap; a.pass = 1; a.counter = h->d_counter + 17;
+        k_astar<<<(unsigned)(warps1 / ASTAR_WARPS_PER_CTA), ASTAR_WARPS_PER_CTA * 32, ASTAR_SMEM_BYTES, st>>>(a);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     return NEO_OK;
 }
 

@@ -45,7 +45,18 @@ def sim():
     return run
 
 
-def test_kernel_source_on_host_matches_reference_paths(golden, sim):
+@pytest.fixture(params=[None, 40], ids=['lists-fit', 'second-pass'])
+def insert_cap(request, monkeypatch):
+    """None: the insertion list / open-list spill hold the whole grid. 40: most searches outgrow the first pass's lists and
+    are re-run by the second pass, as k_astar does with its ASTAR_INSERT_CAP (results must not depend on it)."""
+    if request.param is None:
+        monkeypatch.delenv('NEO_ASTAR_ICAP', raising=False)
+    else:
+        monkeypatch.setenv('NEO_ASTAR_ICAP', str(request.param))
+    return request.param
+
+
+def test_kernel_source_on_host_matches_reference_paths(golden, sim, insert_cap):
     g = golden('geo_M3.npz')
     off = np.concatenate(([0], np.cumsum(g['path_len'])))
     for wid, dn in sorted(set(zip(g['world_id'].tolist(), g['dense'].tolist()))):
@@ -60,7 +71,7 @@ def test_kernel_source_on_host_matches_reference_paths(golden, sim):
                 assert np.array_equal(out['path'][j, :g['path_len'][i]], g['path'][off[i]:off[i + 1]]), (wid, i)
 
 
-def test_kernel_source_on_host_edge_cases(golden, sim):
+def test_kernel_source_on_host_edge_cases(golden, sim, insert_cap):
     g = golden('geo_M3.npz')
     gm = minco_ref.GridMap(g['tiny_occ'], 12, 16, 1.0, 0.0, 0.0)
     out = sim(gm, [[2.5, 2.5]], [[10.5, 6.5]], open_fast=16)

@@ -146,3 +146,25 @@ def test_batch_geo_plan_equals_single_calls():
                              max_attempts=1)
     first = res['attempt'][:32] == 0
     assert first.sum() > 12 and np.array_equal(one['x'][first], res['x'][:32][first])
+
+
+def test_astar_second_pass_gives_the_same_results(monkeypatch):
+    """k_astar's first pass has room for ASTAR_INSERT_CAP inserted nodes per search; searches that outgrow it are re-run
+    by a second pass with full-size lists. With a first pass of 64 / 700 entries (NEO_ASTAR_ICAP, read at neo_create)
+    most / some searches take the second pass: statuses, paths, key nodes and expansion counts must not change."""
+    w = make_world(11)
+    head, tail = make_problems(w, 160, M=6)
+    outs = []
+    for icap in (None, 64, 700):
+        if icap is None:
+            monkeypatch.delenv('NEO_ASTAR_ICAP', raising=False)
+        else:
+            monkeypatch.setenv('NEO_ASTAR_ICAP', str(icap))
+        bp = BatchGeoPlanner(YamlConfig(), max_maps=1)
+        bp.set_map(w)
+        outs.append(bp.handle.astar(head[:, 0], tail[:, 0], max_path=1024))
+        outs.append(bp.handle.astar(head[:, 0], tail[:, 0], max_path=1024))          # scratch left clean by both passes
+    assert outs[0]['closed'].max() > 700                                             # the forced caps are exceeded
+    for o in outs[1:]:
+        for k in ('status', 'path_len', 'closed', 'pruned', 'path'):
+            assert np.array_equal(o[k], outs[0][k]), k
