@@ -160,11 +160,17 @@ X87_FN double x87_to_double(Ext a)
 }
 
 // dnrm2 of v[0..n), elements taken in index order -- the operations exactly as the x87 performs them
+// The summation order is the kernel's (OpenBLAS nrm2.S, disassembled from scipy's bundled library): four accumulators,
+// element i of the leading blocks of 8 goes to accumulator i mod 4, the remaining n mod 8 elements to accumulator 0,
+// total = D + ((C + A) + B). For n < 8 that is the plain sequential sum.
 X87_NOINLINE double x87_nrm2_exact(int n, const double *v)
 {
-    Ext s;
-    s.m = 0; s.e = 0;
-    for (int i = 0; i < n; i++) s = x87_add(s, x87_sqr(x87_from_double(v[i])));
+    Ext acc[4];
+    for (int k = 0; k < 4; k++) { acc[k].m = 0; acc[k].e = 0; }
+    const int nb8 = n & ~7;
+    for (int i = 0; i < nb8; i++) acc[i & 3] = x87_add(acc[i & 3], x87_sqr(x87_from_double(v[i])));
+    for (int i = nb8; i < n; i++) acc[0] = x87_add(acc[0], x87_sqr(x87_from_double(v[i])));
+    const Ext s = x87_add(acc[3], x87_add(x87_add(acc[2], acc[0]), acc[1]));
     return x87_to_double(x87_sqrt(s));
 }
 

@@ -154,6 +154,15 @@ FG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINT
                     C.POINTER(C.c_double))
 
 
+def dnrm2(a):
+    """The restated OpenBLAS dnrm2 (x87 extended arithmetic, four accumulators) on one vector."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    f = lib().orc_dnrm2
+    f.restype = C.c_double
+    f.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    return float(f(a.size, a.ctypes.data_as(C.POINTER(C.c_double))))
+
+
 def lbfgsb_cb(fg, x0):
     """The C restatement of scipy's L-BFGS-B around a Python evaluator fg(x) -> (f, g). Returns (x, nit, nfev, status)."""
     x0 = f64(x0); n = x0.size

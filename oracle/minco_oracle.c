@@ -658,10 +658,17 @@ static double blas_ddot(int n, const double *a, int sa, const double *b, int sb)
     return s;
 }
 
+/* OpenBLAS 0.3.31 dnrm2_k (x86_64 nrm2.S, the kernel every x86_64 target of scipy's bundled library uses; disassembled
+ * from scipy.libs: dnrm2_k_SKYLAKEX): x87 arithmetic in 80-bit extended precision. Four accumulators: blocks of 8
+ * elements feed element i to accumulator i mod 4, the remaining n mod 8 elements all go to accumulator 0, and the sum is
+ * D + ((C + A) + B) before fsqrt and the rounding to double. For n < 8 this is the plain sequential sum. */
 static double blas_dnrm2(int n, const double *a)
 {
-    long double s = 0.0L;
-    for (int i = 0; i < n; i++) { const long double v = a[i]; s += v * v; }
+    long double acc[4] = {0.0L, 0.0L, 0.0L, 0.0L};
+    const int nb = n >> 3;
+    for (int i = 0; i < 8 * nb; i++) { const long double v = a[i]; acc[i & 3] += v * v; }
+    for (int i = 8 * nb; i < n; i++) { const long double v = a[i]; acc[0] += v * v; }
+    const long double s = acc[3] + ((acc[2] + acc[0]) + acc[1]);
     return (double)sqrtl(s);
 }
 
@@ -936,6 +943,8 @@ int orc_lbfgsb(const orc_params *p, const orc_map *map, int M, const double *hea
 
 /* the same optimizer around a caller-supplied evaluator (tests: the reference's own Python get_cost/get_grad) */
 int orc_lbfgsb_cb(int n, const double *x0, orc_fg_fn fg, void *ctx, orc_result *out) { return lbfgsb_run(n, x0, fg, ctx, out); }
+/* the restated BLAS norm alone (tests/test_x87_nrm2.py pins it to scipy's bundled kernel) */
+double orc_dnrm2(int n, const double *a) { return blas_dnrm2(n, a); }
 
 /* ... with every evaluation recorded: x (cap, n), f (cap), g (cap, n); returns the number of evaluations recorded */
 int orc_lbfgsb_traced(const orc_params *p, const orc_map *map, int M, const double *head, const double *tail,

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import scipy
 import scipy.optimize as sopt
-from hypothesis import HealthCheck, given, settings, strategies as st
+from hypothesis import HealthCheck, example, given, settings, strategies as st
 
 from oracle import c_oracle
 
@@ -30,6 +30,9 @@ def openblas_core():
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(n=st.integers(2, 28), seed=st.integers(0, 2**31 - 1), cond=st.floats(0.0, 4.0), quartic=st.floats(0.0, 2.0),
        skew=st.floats(0.0, 0.3))
+# found by this test in round 2: the last trial point differed in one component by one ulp because the restated norm
+# added the squares sequentially; OpenBLAS's x87 kernel uses four accumulators for n >= 8 (tests/test_x87_nrm2.py)
+@example(n=25, seed=25, cond=1.582789709559926, quartic=1.582789709559926, skew=0.0)
 def test_restated_lbfgsb_walks_scipys_iterates(n, seed, cond, quartic, skew):
     rng = np.random.default_rng(seed)
     Q = np.linalg.qr(rng.normal(size=(n, n)))[0]
