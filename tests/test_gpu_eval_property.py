@@ -32,7 +32,7 @@ def handle(cfg_name, tile):
     return _handles[key]
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow], derandomize=True, database=None)
 @given(seed=st.integers(0, 2**31 - 1), M=st.integers(2, 10), cfg_name=st.sampled_from(['yaml', 'default']),
        tile=st.sampled_from([8, 32]), res=st.sampled_from([0.05, 0.1, 0.25]))
 def test_eval_matches_checker_on_random_maps_and_states(seed, M, cfg_name, tile, res):

@@ -27,7 +27,7 @@ def openblas_core():
     return b'?'
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow], derandomize=True, database=None)
 @given(n=st.integers(2, 28), seed=st.integers(0, 2**31 - 1), cond=st.floats(0.0, 4.0), quartic=st.floats(0.0, 2.0),
        skew=st.floats(0.0, 0.3))
 # found by this test in round 2: the last trial point differed in one component by one ulp because the restated norm
