@@ -325,11 +325,13 @@ def e2e_run(torch, dist, run, wl, lib, Ke, distributed, world_size, dev):
     out_host = lib.Handle.alloc_result(B, M)
     hp, tp = lib.pad_state(wl['head']), lib.pad_state(wl['tail'])
 
+    shard = sharding.DeviceShard(h, M, B, world_size, dev, 5) if distributed else None
+
     def step():
-        h.optimize(M, wl['q0'], wl['ts0'], hp, tp, wl['map_ids'], wl['retry_q'], wl['retry_ts'], 5, out=out_host)
-        if distributed:
-            rec = sharding.pack_records(out_host, M)
-            sharding.gather_blocks(rec, [B] * world_size, dev)          # every rank ends with all records, in global order
+        if distributed:     # host inputs -> HBM, kernel, ONE all-gather on the device, ONE D2H of the gathered batch on every rank
+            shard.plan(wl['q0'], wl['ts0'], hp, tp, wl['map_ids'], wl['retry_q'], wl['retry_ts'])
+        else:
+            h.optimize(M, wl['q0'], wl['ts0'], hp, tp, wl['map_ids'], wl['retry_q'], wl['retry_ts'], 5, out=out_host)
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -341,6 +343,7 @@ def e2e_run(torch, dist, run, wl, lib, Ke, distributed, world_size, dev):
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out_host = {k: v[dist.get_rank()] for k, v in shard.views().items()}      # this rank's block of the gathered batch
     return out_host, float(t.item())
 
 
@@ -518,6 +521,8 @@ def main():
     n, nq, M = run.n, 2 * (wl['M'] - 1), wl['M']
     h2d = world_size * (8 * (B * n + 12 * B + B * 4 * nq + M) + (4 * B if wl['map_ids'] is not None else 0))
     d2h = world_size * (8 * B * (n + M + 12 * M + 4) + 4 * B * 6 + 8 * B * 4)
+    if distributed:     # every rank copies the whole gathered batch (world_size blocks) to its host
+        d2h = world_size * world_size * (8 * B * (n + M + 12 * M + 4) + 4 * B * 6)
     assert np.array_equal(out_host['ok'], run.ints()[1].cpu().numpy())      # both paths computed the same thing
 
     peaks = {}
@@ -568,7 +573,7 @@ def main():
                 'ok_fraction': acc['ok_fraction'], 'clocks': clocks, 'map_build_s': map_build_s,
                 'map_build_note': f"{len(wl['worlds'])} occupancy grids -> exact EDT + gradient on the device (neo_set_maps_occupancy: H2D, 5 kernels per map, one sync), outside the timed steps",
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
-                        'includes': 'neo_optimize with host buffers: inputs staged in pinned memory and copied (retry guesses are read over PCIe on demand, counted in full here), kernel, results written by the kernel into mapped pinned memory, scatter into the caller arrays' + (' + pack + NCCL all-gather of the records + D2H of the gathered batch' if distributed else '')},
+                        'includes': 'neo_optimize with host buffers: inputs staged in pinned memory and copied (retry guesses are read over PCIe on demand, counted in full here), kernel, results written by the kernel into mapped pinned memory, scatter into the caller arrays' + (' -- with several ranks: sharding.DeviceShard (inputs staged and copied, neo_optimize_dev, ONE NCCL all-gather of the packed records on the device, ONE D2H of the gathered batch on every rank)' if distributed else '')},
                 'gpu_launches': int(launches) * world_size,
                 'roofline': roofline_of(acc, M, step_ms, fp64_peak, hbm_peak, bool(peaks), hbm_bytes_of(wl), wl['name']),
                 'wall_s_timed_region': t_wall}

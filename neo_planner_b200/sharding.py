@@ -182,3 +182,92 @@ class ShardedPlanner:
             else:
                 full = gather_records(rec, idx, len(head), self.device, counts=[len(s) for s in shares])
         return unpack_records(full, self.M)
+
+
+class DeviceShard:
+    """One rank's equal share (B problems) of a batch, solved through the device-pointer entry point with the records
+    gathered ON THE DEVICE: host inputs -> pinned staging -> HBM, neo_optimize_dev writes ONE packed byte record buffer
+    ([x | ts | coeffs | costs] doubles, then [status ok attempt nit runs nfev] int32), ONE all_gather_into_tensor (NCCL
+    over NVLink) collects the buffers of all ranks, ONE device-to-host copy lands the gathered batch in pinned memory.
+    The host-pointer path (ShardedPlanner + gather_blocks) moves every record over PCIe three times; this one once.
+
+    plan() returns per-field views of the pinned buffer, rank-major: out['x'] has shape (world_size, B, n) -- global
+    order for contiguous equal shards -- valid until the next plan()."""
+
+    def __init__(self, handle, M, B, world_size, device, max_attempts=5):
+        import torch
+        self.torch, self.h, self.M, self.B, self.ws, self.A = torch, handle, M, B, world_size, max_attempts
+        self.dev = torch.device(device)
+        n, nq = 3 * M - 2, 2 * (M - 1)
+        self.n, self.nq = n, nq
+        self.rec_doubles = n + M + 12 * M + 4
+        self.nbytes = B * self.rec_doubles * 8 + B * 6 * 4
+        pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True)
+        self.h_x0, self.h_head, self.h_tail = pin(B, n), pin(B, 6), pin(B, 6)
+        self.h_ids = pin(B, dt=torch.int32)
+        self.h_rq = pin(B, max(max_attempts - 1, 1) * nq)
+        self.h_rtau = pin(M)
+        self.d_x0, self.d_head, self.d_tail = (torch.empty_like(t, device=self.dev) for t in (self.h_x0, self.h_head, self.h_tail))
+        self.d_ids = torch.empty_like(self.h_ids, device=self.dev)
+        self.d_rq = torch.empty_like(self.h_rq, device=self.dev)
+        self.d_rtau = torch.empty_like(self.h_rtau, device=self.dev)
+        self.d_out = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.dev)
+        self.d_all = torch.zeros(world_size * self.nbytes, dtype=torch.uint8, device=self.dev)
+        self.h_all = torch.empty(world_size * self.nbytes, dtype=torch.uint8, pin_memory=True)
+        from . import lib
+        base = self.d_out.data_ptr()
+        off = np.cumsum([0, B * n, B * M, B * 12 * M]) * 8
+        res = lib.Result()
+        res.x, res.ts, res.coeffs, res.costs = (base + int(o) for o in off)
+        ibase = base + B * self.rec_doubles * 8
+        res.status, res.ok, res.attempt, res.nit, res.runs, res.nfev = (ibase + 4 * B * i for i in range(6))
+        res.work = None
+        self.res = res
+
+    def plan(self, q0, ts0, head, tail, map_ids=None, retry_q=None, retry_ts=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import lib
+        torch, h, B, M, n, nq = self.torch, self.h, self.B, self.M, self.n, self.nq
+        tau0, st0 = h.T2tau(np.asarray(ts0, dtype=np.float64).reshape(B, M))          # host libm, like the reference (EP:207-211)
+        if st0.any():
+            raise ValueError('initial durations outside (T_min, T_max): use the host-pointer path, which reports them per problem')
+        x0 = self.h_x0.numpy()
+        x0[:, :nq] = np.asarray(q0, dtype=np.float64).reshape(B, nq); x0[:, nq:] = tau0
+        self.h_head.numpy()[:] = lib.pad_state(head).reshape(B, 6)
+        self.h_tail.numpy()[:] = lib.pad_state(tail).reshape(B, 6)
+        retry_status = 0
+        if self.A > 1:
+            self.h_rq.numpy()[:] = np.asarray(retry_q, dtype=np.float64).reshape(B, -1)
+            rtau, rst = h.T2tau(np.asarray(retry_ts, dtype=np.float64))
+            self.h_rtau.numpy()[:] = rtau
+            retry_status = int(rst.max())
+        if map_ids is not None:
+            self.h_ids.numpy()[:] = map_ids
+        for d, s in ((self.d_x0, self.h_x0), (self.d_head, self.h_head), (self.d_tail, self.h_tail), (self.d_rq, self.h_rq),
+                     (self.d_rtau, self.h_rtau), (self.d_ids, self.h_ids)):
+            d.copy_(s, non_blocking=True)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        h._ck(h.lib.neo_optimize_dev(h.h, B, M, self.d_x0.data_ptr(), None, self.d_head.data_ptr(), self.d_tail.data_ptr(),
+                                     None if map_ids is None else self.d_ids.data_ptr(),
+                                     self.d_rq.data_ptr() if self.A > 1 else None, self.d_rtau.data_ptr() if self.A > 1 else None,
+                                     retry_status, self.A, C.byref(self.res), C.c_void_p(st)))
+        if self.ws > 1:
+            dist.all_gather_into_tensor(self.d_all, self.d_out)
+            self.h_all.copy_(self.d_all, non_blocking=True)
+        else:
+            self.h_all.copy_(self.d_out, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.views()
+
+    def views(self):
+        B, M, n, ws = self.B, self.M, self.n, self.ws
+        raw = self.h_all.numpy().reshape(ws, self.nbytes)
+        dbl = raw[:, :B * self.rec_doubles * 8].view(np.float64)               # (ws, B * rec_doubles)
+        ints = raw[:, B * self.rec_doubles * 8:].view(np.int32).reshape(ws, 6, B)
+        o = np.cumsum([0, B * n, B * M, B * 12 * M, B * 4])
+        out = dict(x=dbl[:, o[0]:o[1]].reshape(ws, B, n), ts=dbl[:, o[1]:o[2]].reshape(ws, B, M),
+                   coeffs=dbl[:, o[2]:o[3]].reshape(ws, B, 6 * M, 2), costs=dbl[:, o[3]:o[4]].reshape(ws, B, 4))
+        for i, k in enumerate(INT_FIELDS):
+            out[k] = ints[:, i]
+        return out

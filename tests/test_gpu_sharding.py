@@ -63,3 +63,31 @@ def test_two_ranks_equal_single_process():
     for r in (0, 1):
         for k in ('x', 'ts', 'coeffs', 'costs', 'status', 'ok', 'nit', 'runs', 'nfev'):
             assert np.array_equal(out[r][k], single[k]), (r, k)
+
+
+def test_device_shard_equals_host_path():
+    """sharding.DeviceShard (device-pointer entry, records packed and gathered on the device, one D2H) against
+    Handle.optimize on the same inputs: every field identical. One rank (NCCL group of size 1 is not needed: the
+    single-rank path copies the packed buffer directly)."""
+    import torch
+    from neo_planner_b200 import guesses, lib
+    cfg = YamlConfig()
+    worlds = [make_world(10 + w) for w in range(2)]
+    heads, tails, ids = [], [], []
+    for slot, w in enumerate(worlds):
+        a, b = make_problems(w, 96)
+        heads.append(a); tails.append(b); ids.append(np.full(96, slot, np.int32))
+    head, tail, ids = np.concatenate(heads), np.concatenate(tails), np.concatenate(ids)
+    B = len(ids)
+    q0, ts0 = guesses.straight_line_guess(cfg, head, tail, M)
+    rq, rts = guesses.retry_guesses(cfg, head, tail, M, 4, rng=np.random.default_rng(3))
+    h = lib.Handle(cfg, 0, len(worlds))
+    for slot, w in enumerate(worlds):
+        h.set_map_occupancy(slot, w.H, w.W, w.res, w.ox, w.oy, w.occ)
+    ref = h.optimize(M, q0, ts0, lib.pad_state(head), lib.pad_state(tail), ids, rq, rts, 5)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        shard = sharding.DeviceShard(h, M, B, 1, 'cuda:0', 5)
+        for _ in range(2):                                                  # buffers are reused between calls
+            out = shard.plan(q0, ts0, head, tail, ids, rq, rts)
+    for k in ('x', 'ts', 'coeffs', 'costs', 'status', 'ok', 'attempt', 'nit', 'runs', 'nfev'):
+        assert np.array_equal(out[k][0], ref[k]), k
