@@ -191,7 +191,7 @@ def handle_with_env(cfg, n_maps, **env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize('M,tile', [(3, 8), (3, 32), (10, 32)])
+@pytest.mark.parametrize('M,tile', [(2, 8), (3, 8), (3, 32), (4, 16), (6, 32), (10, 32)])
 def test_grouped_starts_change_nothing(M, tile):
     """The one-CTA-per-SM variant (warps start their evaluations in groups on named barriers) against the plain one:
     identical outputs problem by problem, for batch sizes that leave most warps without work (1, 7), end inside a group
