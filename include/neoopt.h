@@ -24,7 +24,7 @@
  *   same stream, and maps must not be re-uploaded while a launch is in flight. Use one handle per concurrent stream.
  *   map_ids passed to host-pointer entry points are validated (every id must name a slot that holds a map, else
  *   NEO_ERR_INVALID); for _dev entry points that is a precondition (the ids are in device memory).
- *   Kernel selection: problems with M <= 4 pieces run one per warp below NEO_TILE_MIN_PROBLEMS (8192) problems per call
+ *   Kernel selection: problems with M <= 4 pieces run one per warp below NEO_TILE_MIN_PROBLEMS (12288) problems per call
  *   and 4 (M <= 3) or 2 (M = 4) per warp from there on (one CTA per SM whose warps start their evaluations in groups);
  *   results of the two schedules differ in the last bits of the sampled sums (different partial-sum order), never in
  *   the algorithm. Development switches read from the environment at neo_create (A/B measurements, parity tests):
