@@ -465,7 +465,11 @@ __device__ __forceinline__ int times_from_tau(const Tile<TL> &T, const DevParams
     return bad;
 }
 
-template <int MODE, int TL>
+// COLD: the map cells this evaluation reads are probably not in L2 (a one-shot evaluation of many problems, k_eval):
+// before the sample loop every lane walks its samples once, forming only position -> cell address, and issues an L2
+// prefetch for each, so that the misses overlap instead of being taken one per loop trip (k_eval is bound by exactly
+// that latency: long-scoreboard stalls 43 %). The optimizer's evaluations re-read the same cells ~70 times: not worth it.
+template <int MODE, int TL, bool COLD = false>
 __device__ __forceinline__ void eval_fg(const Tile<TL> &T, const DevParams &P, const MapView &map, const TileMem &m, int M,
                                         double xl, bool want_grad, EvalOut &out, long long *ticks = nullptr)
 {
@@ -515,6 +519,23 @@ __device__ __forceinline__ void eval_fg(const Tile<TL> &T, const DevParams &P, c
     }
 
     NEO_TICK(4);
+    if constexpr (COLD) {
+        for (int i = 0; i < M; i++) {
+            const int ns = (int)m.nsd[2 * i];
+            const double *ci = m.c + 12 * i;
+            double cx[6], cy[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { cx[k] = ci[2 * k]; cy[k] = ci[2 * k + 1]; }
+            for (int j = lane; j < ns; j += TL) {
+                const double t = (double)j * P.dt, t2 = t * t, t4 = t2 * t2;
+                const double px = fma(t4, fma(cx[5], t, cx[4]), fma(t2, fma(cx[3], t, cx[2]), fma(cx[1], t, cx[0])));
+                const double py = fma(t4, fma(cy[5], t, cy[4]), fma(t2, fma(cy[3], t, cy[2]), fma(cy[1], t, cy[0])));
+                const double tr = trunc((py - map.oy) * map.inv_res), tc = trunc((px - map.ox) * map.inv_res);
+                if (tr >= 0.0 && tr < (double)map.H && tc >= 0.0 && tc < (double)map.W)      // a hint: no exact-index fix-up
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(map.cells + ((size_t)(int)tr * map.W + (int)tc)));
+            }
+        }
+    }
     // ---- sampled penalties (EP:392-466) -----------------------------------------------------------------
     double costs2 = 0.0, costs3 = 0.0;
     if constexpr (MODE == SAMPLE_BY_PIECE || MODE == SAMPLE_BY_PIECE_STAGED) {

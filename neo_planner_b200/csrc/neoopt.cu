@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_eval(const DevParams 
         const MapView map = a.maps[a.map_ids ? a.map_ids[b] : 0];
         const double xl = T.tl < n ? a.x[b * n + T.tl] : 0.0;
         EvalOut ev;
-        eval_fg<MODE, TL>(T, P, map, m, M, xl, true, ev);
+        eval_fg<MODE, TL, true>(T, P, map, m, M, xl, true, ev);
         if (T.tl < n) a.grad[b * n + T.tl] = ev.status ? 0.0 : ev.g;
         if (T.tl < 4) a.costs[b * 4 + T.tl] = ev.costs[T.tl];
         if (T.tl == 0) a.status[b] = ev.status;
