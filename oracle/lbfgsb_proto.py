@@ -141,10 +141,15 @@ def ddot(a, b):
     return s
 
 def dnrm2(a):
-    s = np.longdouble(0)
-    for v in a:
-        v = np.longdouble(v); s = s + v * v
-    return float(np.sqrt(s))
+    """OpenBLAS nrm2.S (x87, 80-bit extended = np.longdouble on x86-64): four accumulators -- element i of the leading
+    blocks of 8 goes to accumulator i mod 4, the remaining n mod 8 elements to accumulator 0 -- D + ((C + A) + B), fsqrt."""
+    acc = [np.longdouble(0)] * 4
+    n8 = len(a) & ~7
+    for i, v in enumerate(a):
+        v = np.longdouble(v)
+        k = i & 3 if i < n8 else 0
+        acc[k] = acc[k] + v * v
+    return float(np.sqrt(acc[3] + ((acc[2] + acc[0]) + acc[1])))
 
 def potf2(a, o, n):
     for j in range(n):
