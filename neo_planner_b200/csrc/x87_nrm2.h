@@ -2,8 +2,8 @@
 // for |d| and |y|, see lbfgsb_tile.cuh): every square and the running sum are kept in the x87's 80-bit extended format
 // (64-bit significand, round to nearest even), the square root is taken in that format (fsqrt is correctly rounded) and
 // only the final value is rounded to double. The device has no extended format, so the three operations are carried
-// out on (64-bit significand, exponent) pairs with integer arithmetic. Host-compilable: tests/test_host_logic.py checks
-// it against `long double` arithmetic on the build machine.
+// out on (64-bit significand, exponent) pairs with integer arithmetic. Host-compilable: tests/test_x87_nrm2.py checks
+// it against the real kernel (scipy.linalg.blas.dnrm2) and against `long double` arithmetic on the build machine.
 #pragma once
 #include <stdint.h>
 
