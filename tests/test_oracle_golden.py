@@ -274,7 +274,7 @@ def test_astar_oracle_unreachable_target(golden):
     assert astar_ref.astar_plain(gm, [2.5, 2.5], [10.5, 6.5]) == path
 
 
-@pytest.mark.parametrize('M,count', [(3, 48), (10, 8)])
+@pytest.mark.parametrize('M,count', [(3, 48), (6, 10), (10, 12)])
 def test_lbfgsb_restatement_bit_identical_to_scipy(M, count):
     """scipy's L-BFGS-B (third party, not vendored by the reference) is restated in oracle/minco_oracle.c
     operation by operation -- compact representation (formk / subsm), the BLAS kernels' summation orders, x87 dnrm2.
