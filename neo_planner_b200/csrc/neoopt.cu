@@ -931,7 +931,7 @@ static int launch_optimize(neo_handle *h, OptArgs a, cudaStream_t st)
     switch (a.M) {
 #ifndef NEO_FAST_BUILD      // development builds (-DNEO_FAST_BUILD) instantiate M = 3 only
         case 2: kern = TL == 8 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 2, 8, 3) : NEO_KW(SAMPLE_BY_PIECE, 2); break;
-        case 4: kern = TL == 16 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 4, 16, 2) : NEO_KW(SAMPLE_BY_PIECE, 4); break;
+        case 4: kern = TL == 16 ? NEO_PICK(SAMPLE_BY_PIECE_STAGED, 4, 16, 3) : NEO_KW(SAMPLE_BY_PIECE, 4); break;
         case 5: kern = NEO_KW(SAMPLE_ALL_PIECES, 5); break;
         case 6: kern = NEO_KW(SAMPLE_ALL_PIECES, 6); break;
         case 7: kern = NEO_KW(SAMPLE_ALL_PIECES, 7); break;
