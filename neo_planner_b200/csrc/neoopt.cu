@@ -9,6 +9,8 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -436,6 +438,80 @@ struct MapSlot {
     double res = 0, ox = 0, oy = 0;
 };
 
+// Persistent host worker threads of one handle (neo_optimize's input assembly and result scatter on large batches):
+// created at the first large call, parked on a condition variable in between; spawning threads per call cost ~1 ms of
+// the 5 ms the host side of a 65,536-problem call used to take.
+class HostPool {
+public:
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+        wake_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    // runs fn(begin, end) over [0, count) split into at most NEO_HOST_THREADS parts; the caller works too
+    void run(size_t count, const std::function<void(size_t, size_t)> &fn)
+    {
+        const size_t min_per = 4096;
+        size_t nt = count / min_per;
+        if (nt > NEO_HOST_THREADS) nt = NEO_HOST_THREADS;
+        if (nt <= 1) { fn((size_t)0, count); return; }
+        while (workers_.size() + 1 < nt) workers_.emplace_back([this] { loop(); });
+        const size_t per = (count + nt - 1) / nt;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &fn; count_ = count; per_ = per; parts_ = nt; next_ = 1; pending_ = nt - 1; generation_++;
+        }
+        wake_.notify_all();
+        fn((size_t)0, per < count ? per : count);
+        work();                                            // help with whatever has not been taken yet
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work()
+    {
+        for (;;) {
+            size_t part;
+            const std::function<void(size_t, size_t)> *fn;
+            size_t count, per;
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (!fn_ || next_ >= parts_) return;
+                part = next_++; fn = fn_; count = count_; per = per_;
+            }
+            const size_t b0 = part * per, b1 = b0 + per < count ? b0 + per : count;
+            if (b0 < b1) (*fn)(b0, b1);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                wake_.wait(g, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable wake_, done_;
+    const std::function<void(size_t, size_t)> *fn_ = nullptr;
+    size_t count_ = 0, per_ = 0, parts_ = 0, next_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -461,6 +537,7 @@ struct neo_handle {
     std::mutex mu;
     float last_ms = 0.f;
     long long launches = 0;
+    HostPool pool;                   // host worker threads of neo_optimize
     bool host_timing = false;        // development switch (env NEO_HOST_TIMING): neo_optimize prints its host-side phases
     int grouped = -1, group_warps = 0;   // development switches (env NEO_GROUPED = 0 | 1, NEO_GROUP_WARPS at neo_create; -1 / 0: by batch size)
     int tile = 0;                    // development switch (env NEO_TILE = 8 | 16 | 32 at neo_create; 0: by batch size):
@@ -1168,24 +1245,6 @@ struct TraceHost {
     int32_t *status, *len;
 };
 
-// Splits [0, count) over up to NEO_HOST_THREADS host threads (large batches only) and runs fn(begin, end) on each part.
-template <typename F>
-static void parallel_ranges(size_t count, F fn)
-{
-    const size_t min_per = 4096;
-    size_t nt = count / min_per;
-    if (nt > NEO_HOST_THREADS) nt = NEO_HOST_THREADS;
-    if (nt <= 1) { fn((size_t)0, count); return; }
-    std::vector<std::thread> th;
-    const size_t per = (count + nt - 1) / nt;
-    for (size_t t = 1; t < nt; t++) {
-        const size_t b0 = t * per, b1 = b0 + per < count ? b0 + per : count;
-        if (b0 < b1) th.emplace_back([=] { fn(b0, b1); });
-    }
-    fn((size_t)0, per < count ? per : count);
-    for (auto &t : th) t.join();
-}
-
 // Host-buffer entry: inputs are assembled in ONE pinned staging buffer that mirrors the device layout
 // (x0 = [q0, map_T2tau(ts0)], EP:207-211) in three stages, each copied while the next is assembled; results are written
 // by the kernel straight into the same pinned buffer (mapped) and scattered into the caller's arrays once it ends. For
@@ -1234,7 +1293,7 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     std::atomic<int> any_bad_flag{0};
     // three stages, each copied to the device while the next one is assembled
     cudaStream_t st = h->stream;
-    parallel_ranges(b, [&](size_t i0, size_t i1) {
+    h->pool.run(b, [&](size_t i0, size_t i1) {
         bool bad = false;
         for (size_t i = i0; i < i1; i++) {
             memcpy(&hx0[i * n], q0 + i * nq, sizeof(double) * nq);
@@ -1252,7 +1311,7 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     });
     CK(cudaMemcpyAsync(dbase + L.x0, hbase + L.x0, L.head - L.x0, cudaMemcpyHostToDevice, st));
     const bool any_bad = any_bad_flag.load() != 0;
-    parallel_ranges(b, [&](size_t i0, size_t i1) {
+    h->pool.run(b, [&](size_t i0, size_t i1) {
         memcpy(hbase + L.head + 48 * i0, head + i0 * 6, 48 * (i1 - i0));
         memcpy(hbase + L.tail + 48 * i0, tail + i0 * 6, 48 * (i1 - i0));
         if (map_ids) memcpy(hbase + L.ids + 4 * i0, map_ids + i0, 4 * (i1 - i0));
@@ -1265,7 +1324,7 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     // the retry guesses (the largest input: 4 per problem) stay in the pinned buffer: only the problems that do retry
     // read theirs, through the mapped pointer, when the retry starts
     if (A1)
-        parallel_ranges(b, [&](size_t i0, size_t i1) {
+        h->pool.run(b, [&](size_t i0, size_t i1) {
             memcpy(hbase + L.rq + 8 * i0 * A1 * nq, retry_q + i0 * A1 * nq, 8 * (i1 - i0) * A1 * nq);
         });
     // results: the kernel writes every resolved problem's record straight into the pinned staging buffer (mapped host
@@ -1315,7 +1374,7 @@ static int optimize_host(neo_handle *h, int B, int M, const double *q0, const do
     CK(cudaStreamSynchronize(st));
     const auto t_done = now();
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    parallel_ranges(b, [&](size_t i0, size_t i1) {
+    h->pool.run(b, [&](size_t i0, size_t i1) {
         const size_t c = i1 - i0;
         memcpy(out->x + i0 * n, hbase + L.x + 8 * i0 * n, 8 * c * n);
         memcpy(out->ts + i0 * M, hbase + L.ts + 8 * i0 * M, 8 * c * M);
