@@ -58,7 +58,8 @@ def run_traced(M, B, tile, world_id=0, cap=640):
     return cfg, w, head, tail, q0, ts0, rq, rts, h, out, tr
 
 
-@pytest.mark.parametrize('M,B,tile', [(3, 256, 32), (3, 256, 8), (2, 64, 8), (4, 64, 16), (10, 48, 32)])
+@pytest.mark.parametrize('M,B,tile', [(3, 256, 32), (3, 256, 8), (2, 64, 8), (4, 64, 16), (5, 48, 32), (6, 48, 32), (7, 32, 32), (8, 32, 32),
+                                      (9, 32, 32), (10, 48, 32)])
 def test_device_optimizer_in_lockstep_with_the_checker(M, B, tile):
     cfg, w, head, tail, q0, ts0, rq, rts, h, out, tr = run_traced(M, B, tile)
     A = 5
