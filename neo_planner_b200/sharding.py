@@ -184,6 +184,37 @@ class ShardedPlanner:
         return unpack_records(full, self.M)
 
 
+def packed_record_bytes(B: int, M: int) -> int:
+    """Bytes of one rank's packed record buffer: [x | ts | coeffs | costs] doubles, then 6 int32 fields, B problems."""
+    return B * ((3 * M - 2) + M + 12 * M + 4) * 8 + B * len(INT_FIELDS) * 4
+
+
+def packed_record_offsets(B: int, M: int):
+    """Byte offsets of the fields inside one rank's packed record buffer (the layout neo_optimize_dev is pointed at)."""
+    n = 3 * M - 2
+    d = np.cumsum([0, B * n, B * M, B * 12 * M, B * 4]) * 8
+    off = dict(x=int(d[0]), ts=int(d[1]), coeffs=int(d[2]), costs=int(d[3]))
+    for i, k in enumerate(INT_FIELDS):
+        off[k] = int(d[4]) + 4 * B * i
+    return off
+
+
+def split_packed_records(raw: np.ndarray, B: int, M: int):
+    """(world_size, packed_record_bytes) uint8 -> per-field views, rank-major: x (ws, B, n), ts (ws, B, M), coeffs
+    (ws, B, 6M, 2), costs (ws, B, 4), and the int32 fields (ws, B). No copies."""
+    ws = raw.shape[0]
+    n = 3 * M - 2
+    nd = B * (n + M + 12 * M + 4)
+    dbl = raw[:, :nd * 8].view(np.float64)
+    ints = raw[:, nd * 8:].view(np.int32).reshape(ws, len(INT_FIELDS), B)
+    o = np.cumsum([0, B * n, B * M, B * 12 * M, B * 4])
+    out = dict(x=dbl[:, o[0]:o[1]].reshape(ws, B, n), ts=dbl[:, o[1]:o[2]].reshape(ws, B, M),
+               coeffs=dbl[:, o[2]:o[3]].reshape(ws, B, 6 * M, 2), costs=dbl[:, o[3]:o[4]].reshape(ws, B, 4))
+    for i, k in enumerate(INT_FIELDS):
+        out[k] = ints[:, i]
+    return out
+
+
 class DeviceShard:
     """One rank's equal share (B problems) of a batch, solved through the device-pointer entry point with the records
     gathered ON THE DEVICE: host inputs -> pinned staging -> HBM, neo_optimize_dev writes ONE packed byte record buffer
@@ -200,8 +231,7 @@ class DeviceShard:
         self.dev = torch.device(device)
         n, nq = 3 * M - 2, 2 * (M - 1)
         self.n, self.nq = n, nq
-        self.rec_doubles = n + M + 12 * M + 4
-        self.nbytes = B * self.rec_doubles * 8 + B * 6 * 4
+        self.nbytes = packed_record_bytes(B, M)
         pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True)
         self.h_x0, self.h_head, self.h_tail = pin(B, n), pin(B, 6), pin(B, 6)
         self.h_ids = pin(B, dt=torch.int32)
@@ -216,11 +246,9 @@ class DeviceShard:
         self.h_all = torch.empty(world_size * self.nbytes, dtype=torch.uint8, pin_memory=True)
         from . import lib
         base = self.d_out.data_ptr()
-        off = np.cumsum([0, B * n, B * M, B * 12 * M]) * 8
         res = lib.Result()
-        res.x, res.ts, res.coeffs, res.costs = (base + int(o) for o in off)
-        ibase = base + B * self.rec_doubles * 8
-        res.status, res.ok, res.attempt, res.nit, res.runs, res.nfev = (ibase + 4 * B * i for i in range(6))
+        for k, o in packed_record_offsets(B, M).items():
+            setattr(res, k, base + o)
         res.work = None
         self.res = res
 
@@ -261,13 +289,4 @@ class DeviceShard:
         return self.views()
 
     def views(self):
-        B, M, n, ws = self.B, self.M, self.n, self.ws
-        raw = self.h_all.numpy().reshape(ws, self.nbytes)
-        dbl = raw[:, :B * self.rec_doubles * 8].view(np.float64)               # (ws, B * rec_doubles)
-        ints = raw[:, B * self.rec_doubles * 8:].view(np.int32).reshape(ws, 6, B)
-        o = np.cumsum([0, B * n, B * M, B * 12 * M, B * 4])
-        out = dict(x=dbl[:, o[0]:o[1]].reshape(ws, B, n), ts=dbl[:, o[1]:o[2]].reshape(ws, B, M),
-                   coeffs=dbl[:, o[2]:o[3]].reshape(ws, B, 6 * M, 2), costs=dbl[:, o[3]:o[4]].reshape(ws, B, 4))
-        for i, k in enumerate(INT_FIELDS):
-            out[k] = ints[:, i]
-        return out
+        return split_packed_records(self.h_all.numpy().reshape(self.ws, self.nbytes), self.B, self.M)

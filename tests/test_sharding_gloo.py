@@ -99,3 +99,31 @@ def test_two_rank_gather_matches_single_process(shuffle):
                 assert out[r][k].shape == ref.shape
                 continue
             assert np.array_equal(out[r][k], ref), (r, k)
+
+
+def test_packed_record_layout_round_trip():
+    """The byte layout sharding.DeviceShard points neo_optimize_dev at (one buffer per rank, gathered with one
+    collective) against the field arrays it is split back into: written through the offsets, read through the views."""
+    B, ws = 37, 3
+    rng = np.random.default_rng(4)
+    n = 3 * M - 2
+    nbytes = sharding.packed_record_bytes(B, M)
+    off = sharding.packed_record_offsets(B, M)
+    raw = np.zeros((ws, nbytes), np.uint8)
+    want = []
+    for r in range(ws):
+        f = dict(x=rng.normal(size=(B, n)), ts=rng.uniform(1, 4, size=(B, M)), coeffs=rng.normal(size=(B, 6 * M, 2)),
+                 costs=rng.normal(size=(B, 4)))
+        for k in sharding.INT_FIELDS:
+            f[k] = rng.integers(-5, 500, size=B).astype(np.int32)
+        for k, a in f.items():
+            b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+            raw[r, off[k]:off[k] + b.size] = b
+        want.append(f)
+    # the fields tile the buffer exactly, in the order [x | ts | coeffs | costs | int fields]
+    ends = sorted((off[k], off[k] + np.ascontiguousarray(want[0][k]).nbytes) for k in off)
+    assert ends[0][0] == 0 and ends[-1][1] == nbytes and all(a[1] == b[0] for a, b in zip(ends, ends[1:]))
+    got = sharding.split_packed_records(raw, B, M)
+    for r in range(ws):
+        for k, a in want[r].items():
+            assert np.array_equal(got[k][r], a), (r, k)
