@@ -216,6 +216,9 @@ int neo_launch_count(neo_handle *h, int64_t *count);
 /* test hooks: the double-double exp used for tau -> T, on the device and as compiled for the host */
 int neo_test_exp_dev(neo_handle *h, int n, const double *x, double *y);
 int neo_test_exp_host(int n, const double *x, double *y);
+/* test hook (no GPU needed): `calls` runs of the host worker pool that neo_optimize uses, over [0, count); returns the number
+ * of indices not visited exactly once per run. */
+int neo_test_host_pool(long long count, int calls);
 
 #ifdef __cplusplus
 }

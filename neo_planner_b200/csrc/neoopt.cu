@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -1723,6 +1724,21 @@ extern "C" int neo_test_opt_ticks(long long *out)
     return NEO_OK;
 }
 #endif
+
+// test hook (no GPU needed): `calls` runs of the host worker pool over [0, count); every index must be visited exactly once
+// per run. Returns the number of indices whose visit count is wrong.
+extern "C" int neo_test_host_pool(long long count, int calls)
+{
+    HostPool pool;
+    std::vector<unsigned char> hits((size_t)count);
+    long long bad = 0;
+    for (int c = 0; c < calls; c++) {
+        std::fill(hits.begin(), hits.end(), 0);
+        pool.run((size_t)count, [&](size_t i0, size_t i1) { for (size_t i = i0; i < i1; i++) hits[i]++; });
+        for (size_t i = 0; i < (size_t)count; i++) bad += hits[i] != 1;
+    }
+    return bad > 0x7fffffff ? 0x7fffffff : (int)bad;
+}
 
 extern "C" int neo_test_exp_host(int n, const double *x, double *y)
 {

@@ -46,7 +46,7 @@ class Result(C.Structure):
 EXPORTS = ['neo_create', 'neo_destroy', 'neo_set_config', 'neo_last_error', 'neo_device_info', 'neo_set_map_esdf',
            'neo_set_map_occupancy', 'neo_set_maps_occupancy', 'neo_set_map_points', 'neo_get_occupancy', 'neo_get_map', 'neo_query_map', 'neo_eval', 'neo_eval_dev', 'neo_optimize',
            'neo_optimize_dev', 'neo_optimize_trace', 'neo_T2tau', 'neo_get_coeffs', 'neo_sample', 'neo_last_kernel_ms', 'neo_fp64_peak',
-           'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host', 'neo_astar', 'neo_astar_dev']
+           'neo_launch_count', 'neo_test_exp_dev', 'neo_test_exp_host', 'neo_test_host_pool', 'neo_astar', 'neo_astar_dev']
 
 _lib = None
 

@@ -296,3 +296,15 @@ def test_clamp_durations_flags_out_of_range_predictions():
     out, touched = frames.clamp_durations(ts, 0.5, 5.0)
     assert touched.tolist() == [False, True, True] and np.array_equal(out[0], ts[0])
     assert ((out > 0.5) & (out < 5.0)).all()
+
+
+def test_host_worker_pool_covers_every_index_once():
+    """neo_optimize assembles inputs and scatters results of a large batch on a persistent pool of host threads
+    (csrc/neoopt.cu: HostPool). The test hook runs the pool without a GPU: over many calls and sizes -- below the
+    threading threshold, not divisible by the thread count, large -- every index is visited exactly once per call."""
+    import ctypes
+    l = lib.load()
+    l.neo_test_host_pool.argtypes = [ctypes.c_longlong, ctypes.c_int]
+    l.neo_test_host_pool.restype = ctypes.c_int
+    for count, calls in ((1, 3), (4095, 3), (8192, 50), (65536, 200), (65537, 50), (100003, 50), (1 << 20, 10)):
+        assert l.neo_test_host_pool(count, calls) == 0, count
